@@ -1,0 +1,55 @@
+// Context lifecycle and shared C-ABI entry points.
+#include "common.cuh"
+
+extern "C" int b2_version(void) { return 100; }
+
+extern "C" int b2_create(int device, b2_context** out) {
+  if (!out) return B2_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return B2_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2_ERR_CUDA;
+  if (prop.major != 10) return B2_ERR_STATE;  // sm_100a cubins only: fail loudly on anything else
+  if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
+  b2_context* ctx = new b2_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return B2_ERR_CUDA;
+  }
+  *out = ctx;
+  return B2_OK;
+}
+
+extern "C" void b2_destroy(b2_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  sp_destroy(ctx);
+  lg_destroy(ctx);
+  sg_destroy(ctx);
+  rs_destroy(ctx);
+  for (auto& b : ctx->stage_d) b.release();
+  for (auto& b : ctx->stage_h) b.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* b2_last_error(const b2_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" uint64_t b2_launch_count(const b2_context* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host_out, int64_t max_floats) {
+  if (!ctx || !name || !host_out) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->debug.find(name);
+  if (it == ctx->debug.end()) return b2_fail(ctx, B2_ERR_ARG, std::string("no debug buffer named ") + name);
+  int64_t n = it->second.n < max_floats ? it->second.n : max_floats;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(host_out, it->second.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return b2_fail(ctx, B2_ERR_CUDA, "debug fetch copy failed");
+  return n;
+}

@@ -1,0 +1,131 @@
+// Shared context / helpers for libgtsfm_b200.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gtsfm_b200.h"
+
+#define B2_OK 0
+#define B2_ERR_CUDA -1
+#define B2_ERR_ARG -2
+#define B2_ERR_STATE -3
+
+struct DevBuf {  // grow-only device allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostBuf {  // grow-only pinned host allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct DebugView {
+  const float* p;
+  int64_t n;
+};
+
+struct SuperPointState;
+struct LightGlueState;
+struct SuperGlueState;
+struct RansacState;
+
+struct b2_context {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  std::mutex mu;
+  uint64_t launches = 0;
+  cudaStream_t stream = nullptr;  // owned; used by *_host entry points
+  std::map<std::string, DebugView> debug;
+  SuperPointState* sp = nullptr;
+  LightGlueState* lg = nullptr;
+  SuperGlueState* sg = nullptr;
+  RansacState* rs = nullptr;
+  // staging shared by the *_host entry points
+  DevBuf stage_d[8];
+  HostBuf stage_h[4];
+};
+
+inline int b2_fail(b2_context* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define B2_CUDA(ctx, expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      return b2_fail(ctx, B2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +       \
+                                           " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                             \
+  } while (0)
+
+// launch bookkeeping: every kernel launch of the library goes through this macro
+#define B2_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)  \
+  do {                                                          \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+    (ctx)->launches++;                                          \
+  } while (0)
+
+#define B2_CHECK_LAUNCH(ctx) B2_CUDA(ctx, cudaGetLastError())
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// model state lifecycle (defined in the respective .cu files)
+void sp_destroy(b2_context* ctx);
+void lg_destroy(b2_context* ctx);
+void sg_destroy(b2_context* ctx);
+void rs_destroy(b2_context* ctx);
+
+// shared device helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

@@ -1,0 +1,700 @@
+// SuperPoint detect + describe for sm_100a.
+//
+// Reference semantics restated (file:line relative to the reference repo):
+//   thirdparty/SuperGluePretrainedNetwork/models/superpoint.py:145-202 (forward), :47-62 (simple_nms),
+//   :65-70 (remove_borders), :80-92 (sample_descriptors); wrapper gtsfm/frontend/detector_descriptor/superpoint.py:63-93
+//   and gtsfm/utils/images.py:15-40 (cv2 RGB->gray).
+//
+// Data layout in HBM: activations NHWC fp32 (channel-contiguous: one pixel's 64/128/256 channels are one 256/512/1024 B
+// segment, which is what both the implicit-GEMM K loop and the bilinear descriptor gather want); conv weights repacked
+// at load to [tap][cin][cout]; 1x1 weights to [cin][cout]; score / NMS maps (H8, W8) fp32; dense descriptors
+// (Hc, Wc, 256) fp32; keypoints as (x, y) float pairs in torch.nonzero (row-major) order.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SP_NCONV = 12;
+// name order: conv1a conv1b conv2a conv2b conv3a conv3b conv4a conv4b convPa convPb convDa convDb
+constexpr int SP_CO[SP_NCONV] = {64, 64, 64, 64, 128, 128, 128, 128, 256, 65, 256, 256};
+constexpr int SP_CI[SP_NCONV] = {1, 64, 64, 64, 64, 128, 128, 128, 128, 256, 128, 256};
+constexpr int SP_K[SP_NCONV] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 3, 1};
+constexpr size_t SP_NFLOATS = 1300865;
+
+}  // namespace
+
+struct SuperPointState {
+  bool loaded = false;
+  DevBuf wblob;
+  float* w[SP_NCONV] = {};
+  float* b[SP_NCONV] = {};
+  // workspace
+  DevBuf gray, a0, a1, feat, head, heat, nms, rowcnt, rowoff, dense, kpxy, kpsc;
+  int H = 0, W = 0, Hc = 0, Wc = 0;
+  int n_kp = 0;
+  bool have_dense = false;
+};
+
+void sp_destroy(b2_context* ctx) {
+  if (!ctx->sp) return;
+  SuperPointState* s = ctx->sp;
+  DevBuf* bufs[] = {&s->wblob, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
+                    &s->rowcnt, &s->rowoff, &s->dense, &s->kpxy, &s->kpsc};
+  for (DevBuf* b : bufs) b->release();
+  delete s;
+  ctx->sp = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+
+// cv2 COLOR_RGB2GRAY / COLOR_RGBA2GRAY for 8-bit: (9798 R + 19235 G + 3735 B + 2^14) >> 15   (utils/images.py:36-38)
+__global__ void k_to_gray(const uint8_t* __restrict__ img, size_t pitch, int channels, int H, int W,
+                          uint8_t* __restrict__ gray) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= W) return;
+  const uint8_t* p = img + (size_t)y * pitch + (size_t)x * channels;
+  uint8_t g;
+  if (channels == 1) {
+    g = p[0];
+  } else {
+    int v = 9798 * (int)p[0] + 19235 * (int)p[1] + 3735 * (int)p[2] + (1 << 14);
+    g = (uint8_t)(v >> 15);
+  }
+  gray[(size_t)y * W + x] = g;
+}
+
+// conv1a: 1 -> 64 channels, 3x3, pad 1, bias, ReLU; input gray u8 / 255 (gtsfm/.../superpoint.py:74).
+// block = 256 threads = 16 pixels x 16 channel groups of 4.
+__global__ void __launch_bounds__(256) k_conv1a(const uint8_t* __restrict__ gray, const float* __restrict__ wt /*[9][64]*/,
+                                                 const float* __restrict__ bias, float* __restrict__ out, int H, int W) {
+  __shared__ float ws[9 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) ws[i] = wt[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  long long pix = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  int cg = threadIdx.x & 15;
+  if (pix >= (long long)H * W) return;
+  int y = (int)(pix / W), x = (int)(pix % W);
+  float acc[4] = {bs[cg * 4 + 0], bs[cg * 4 + 1], bs[cg * 4 + 2], bs[cg * 4 + 3]};
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = (float)gray[(size_t)yy * W + xx] / 255.0f;
+      const float* wp = &ws[((dy + 1) * 3 + (dx + 1)) * 64 + cg * 4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+    }
+  }
+  float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  *reinterpret_cast<float4*>(out + (size_t)pix * 64 + cg * 4) = o;
+}
+
+// Generic 3x3 conv, pad 1, bias + ReLU, optional fused 2x2/2 max-pool, NHWC fp32, SIMT fp32 FMA (exact-fp32 path).
+// Block tile: 8 rows x 16 cols of pixels x 64 output channels; thread micro-tile 2x4 pixels x 4 channels.
+constexpr int CT_H = 8, CT_W = 16, CK = 8, CKP = 12;  // CKP: padded per-pixel stride in smem (floats)
+template <int POOL>
+__global__ void __launch_bounds__(256) k_conv3x3(const float* __restrict__ in, const float* __restrict__ wt,
+                                                  const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                                                  int Cin, int Cout) {
+  __shared__ __align__(16) float in_s[(CT_H + 2) * (CT_W + 2) * CKP];
+  __shared__ __align__(16) float w_s[9 * CK * 64];
+  const int t = threadIdx.x;
+  const int cg = t & 15, pg = t >> 4;
+  const int prow = (pg >> 2) * 2, pcol = (pg & 3) * 4;
+  const int y0 = blockIdx.y * CT_H, x0 = blockIdx.x * CT_W;
+  const int co0 = blockIdx.z * 64;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += CK) {
+    // input patch (10 x 18 pixels x CK channels), zero padded
+    for (int i = t; i < (CT_H + 2) * (CT_W + 2) * (CK / 4); i += 256) {
+      int q = i % (CK / 4);
+      int p = i / (CK / 4);
+      int py = p / (CT_W + 2), px = p % (CT_W + 2);
+      int yy = y0 + py - 1, xx = x0 + px - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = *reinterpret_cast<const float4*>(in + ((size_t)yy * W + xx) * Cin + c0 + q * 4);
+      *reinterpret_cast<float4*>(&in_s[p * CKP + q * 4]) = v;
+    }
+    // weights [tap][c0..c0+CK)[co0..co0+64)
+    for (int i = t; i < 9 * CK * 16; i += 256) {
+      int q = i & 15;
+      int k = (i >> 4) % CK;
+      int tap = i / (16 * CK);
+      *reinterpret_cast<float4*>(&w_s[(tap * CK + k) * 64 + q * 4]) =
+          *reinterpret_cast<const float4*>(wt + ((size_t)tap * Cin + c0 + k) * Cout + co0 + q * 4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+      for (int k4 = 0; k4 < CK / 4; ++k4) {
+        float4 wv[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          wv[kk] = *reinterpret_cast<const float4*>(&w_s[(tap * CK + k4 * 4 + kk) * 64 + cg * 4]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 a = *reinterpret_cast<const float4*>(
+                &in_s[((prow + i + dy) * (CT_W + 2) + (pcol + j + dx)) * CKP + k4 * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              acc[i][j][0] = fmaf(av[kk], wv[kk].x, acc[i][j][0]);
+              acc[i][j][1] = fmaf(av[kk], wv[kk].y, acc[i][j][1]);
+              acc[i][j][2] = fmaf(av[kk], wv[kk].z, acc[i][j][2]);
+              acc[i][j][3] = fmaf(av[kk], wv[kk].w, acc[i][j][3]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const float4 bv = *reinterpret_cast<const float4*>(bias + co0 + cg * 4);
+  const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+  if (POOL == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int yy = y0 + prow + i, xx = x0 + pcol + j;
+        if (yy < H && xx < W) {
+          float4 o = make_float4(fmaxf(acc[i][j][0] + bb[0], 0.f), fmaxf(acc[i][j][1] + bb[1], 0.f),
+                                 fmaxf(acc[i][j][2] + bb[2], 0.f), fmaxf(acc[i][j][3] + bb[3], 0.f));
+          *reinterpret_cast<float4*>(out + ((size_t)yy * W + xx) * Cout + co0 + cg * 4) = o;
+        }
+      }
+  } else {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int yo = (y0 + prow) >> 1;
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+      int xo = ((x0 + pcol) >> 1) + jp;
+      if (yo < Ho && xo < Wo) {
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float m = fmaxf(fmaxf(acc[0][2 * jp][c], acc[0][2 * jp + 1][c]), fmaxf(acc[1][2 * jp][c], acc[1][2 * jp + 1][c]));
+          o[c] = fmaxf(m + bb[c], 0.f);  // max commutes with the monotone bias-add + ReLU
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)yo * Wo + xo) * Cout + co0 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// convPb (1x1, 256 -> 65) + softmax over 65 + drop dustbin + depth-to-space (superpoint.py:162-166).
+// block = 128 threads, 16 cells.
+constexpr int PB_CELLS = 16;
+__global__ void __launch_bounds__(128) k_head_scores(const float* __restrict__ cpa /*[cells][256]*/,
+                                                      const float* __restrict__ wt /*[256][65]*/,
+                                                      const float* __restrict__ bias, float* __restrict__ heat, int Hc,
+                                                      int Wc) {
+  __shared__ float xs[PB_CELLS][256];
+  __shared__ float lg[PB_CELLS][66];
+  const int t = threadIdx.x;
+  const int ncell = Hc * Wc;
+  const int cell0 = blockIdx.x * PB_CELLS;
+  for (int i = t; i < PB_CELLS * 64; i += 128) {
+    int c = i >> 6, q = i & 63;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cell0 + c < ncell) v = *reinterpret_cast<const float4*>(cpa + (size_t)(cell0 + c) * 256 + q * 4);
+    *reinterpret_cast<float4*>(&xs[c][q * 4]) = v;
+  }
+  __syncthreads();
+  if (t < 65) {
+    float acc[PB_CELLS];
+    const float b = bias[t];
+#pragma unroll
+    for (int c = 0; c < PB_CELLS; ++c) acc[c] = b;
+    for (int k = 0; k < 256; ++k) {
+      float w = wt[k * 65 + t];
+#pragma unroll
+      for (int c = 0; c < PB_CELLS; ++c) acc[c] = fmaf(xs[c][k], w, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < PB_CELLS; ++c) lg[c][t] = acc[c];
+  }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int c = warp; c < PB_CELLS; c += 4) {
+    int cell = cell0 + c;
+    if (cell >= ncell) break;
+    float v0 = lg[c][lane], v1 = lg[c][lane + 32], v2 = lane == 0 ? lg[c][64] : -INFINITY;
+    float m = warp_max(fmaxf(fmaxf(v0, v1), v2));
+    float e0 = expf(v0 - m), e1 = expf(v1 - m), e2 = lane == 0 ? expf(v2 - m) : 0.f;
+    float s = warp_sum(e0 + e1 + e2);
+    int r = cell / Wc, cc = cell % Wc;
+    int W8 = Wc * 8;
+    // channel k -> pixel (8r + k/8, 8c + k%8)
+    heat[(size_t)(8 * r + (lane >> 3)) * W8 + 8 * cc + (lane & 7)] = e0 / s;
+    heat[(size_t)(8 * r + 4 + (lane >> 3)) * W8 + 8 * cc + (lane & 7)] = e1 / s;
+  }
+}
+
+// simple_nms with radius 4 (superpoint.py:47-62), fused over a tile with a 20-pixel halo, followed by the
+// threshold + border test (superpoint.py:170-178) feeding per-row keypoint counts.
+constexpr int NT_W = 64, NT_H = 32, NR = 4, NHALO = 5 * NR;
+constexpr int NRW = NT_W + 2 * NHALO, NRH = NT_H + 2 * NHALO;  // 104 x 72
+constexpr int NREG = NRW * NRH;
+
+__device__ __forceinline__ void pool9_f(const float* __restrict__ src, float* __restrict__ tmp, float* __restrict__ dst) {
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = i % NRW, y = i / NRW;
+    float m = -INFINITY;
+    int xa = max(x - NR, 0), xb = min(x + NR, NRW - 1);
+    for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, src[y * NRW + xx]);
+    tmp[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = i % NRW, y = i / NRW;
+    float m = -INFINITY;
+    int ya = max(y - NR, 0), yb = min(y + NR, NRH - 1);
+    for (int yy = ya; yy <= yb; ++yy) m = fmaxf(m, tmp[yy * NRW + x]);
+    dst[i] = m;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void dilate9_b(const uint8_t* __restrict__ src, uint8_t* __restrict__ tmp, uint8_t* __restrict__ dst) {
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = i % NRW, y = i / NRW;
+    uint8_t m = 0;
+    int xa = max(x - NR, 0), xb = min(x + NR, NRW - 1);
+    for (int xx = xa; xx <= xb; ++xx) m |= src[y * NRW + xx];
+    tmp[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = i % NRW, y = i / NRW;
+    uint8_t m = 0;
+    int ya = max(y - NR, 0), yb = min(y + NR, NRH - 1);
+    for (int yy = ya; yy <= yb; ++yy) m |= tmp[yy * NRW + x];
+    dst[i] = m;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_nms(const float* __restrict__ heat, float* __restrict__ nms, int H8, int W8,
+                                              float thr, int border, int* __restrict__ rowcnt) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* S = reinterpret_cast<float*>(smraw);  // scores (-inf outside the image)
+  float* T = S + NREG;                         // scratch
+  float* X = T + NREG;                         // pooled scores
+  float* T2 = X + NREG;                        // scratch
+  uint8_t* M = reinterpret_cast<uint8_t*>(T2 + NREG);  // max_mask
+  uint8_t* P = M + NREG;                              // scratch
+  uint8_t* Q = P + NREG;                              // supp_mask
+  const int x0 = blockIdx.x * NT_W - NHALO, y0 = blockIdx.y * NT_H - NHALO;
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = x0 + i % NRW, y = y0 + i / NRW;
+    S[i] = (x >= 0 && x < W8 && y >= 0 && y < H8) ? heat[(size_t)y * W8 + x] : -INFINITY;
+  }
+  __syncthreads();
+  pool9_f(S, T, X);
+  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+    int x = x0 + i % NRW, y = y0 + i / NRW;
+    bool inside = (x >= 0 && x < W8 && y >= 0 && y < H8);
+    M[i] = (inside && S[i] == X[i]) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int it = 0; it < 2; ++it) {
+    dilate9_b(M, P, Q);  // supp_mask = max_pool(max_mask) > 0
+    for (int i = threadIdx.x; i < NREG; i += blockDim.x) T[i] = Q[i] ? (S[i] == -INFINITY ? -INFINITY : 0.f) : S[i];
+    __syncthreads();
+    pool9_f(T, T2, X);  // supp_scores in T, pooled into X
+    for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
+      bool fresh = (T[i] == X[i]) && !Q[i] && S[i] != -INFINITY;
+      M[i] = M[i] | (fresh ? 1 : 0);
+    }
+    __syncthreads();
+  }
+  // central tile: where(max_mask, scores, 0) + count survivors of threshold / border per row
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NT_W * NT_H; i += blockDim.x) {
+    int tx = i % NT_W, ty = i / NT_W;
+    int x = blockIdx.x * NT_W + tx, y = blockIdx.y * NT_H + ty;
+    bool inside = x < W8 && y < H8;
+    float v = 0.f;
+    if (inside) {
+      int r = (ty + NHALO) * NRW + tx + NHALO;
+      v = M[r] ? S[r] : 0.f;
+      nms[(size_t)y * W8 + x] = v;
+    }
+    bool kp = inside && v > thr && y >= border && y < H8 - border && x >= border && x < W8 - border;
+    unsigned m = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0 && m) atomicAdd(&rowcnt[y], __popc(m));  // a warp covers 32 consecutive x of one row (NT_W = 64)
+  }
+}
+
+// exclusive scan of per-row counts (H8 <= a few thousand): single block.
+__global__ void __launch_bounds__(1024) k_scan_rows(const int* __restrict__ cnt, int* __restrict__ off, int n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < n ? cnt[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    if (lane == 31) warp_tot[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+      int ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += u;
+      }
+      warp_tot[lane] = ws - w;  // exclusive
+    }
+    __syncthreads();
+    int excl = carry + warp_tot[warp] + s - v;
+    if (i < n) off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[n] = carry;
+}
+
+// ordered compaction: one warp per row, keypoints in ascending x; (x, y) float pairs (superpoint.py:187 flip).
+__global__ void __launch_bounds__(256) k_compact(const float* __restrict__ nms, int H8, int W8, float thr, int border,
+                                                  const int* __restrict__ rowoff, float* __restrict__ xy,
+                                                  float* __restrict__ score, int cap) {
+  int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (y >= H8 || y < border || y >= H8 - border) return;
+  int off = rowoff[y];
+  if (rowoff[y + 1] == off) return;
+  for (int xb = 0; xb < W8; xb += 32) {
+    int x = xb + lane;
+    float v = x < W8 ? nms[(size_t)y * W8 + x] : 0.f;
+    bool kp = v > thr && x >= border && x < W8 - border;
+    unsigned m = __ballot_sync(0xffffffffu, kp);
+    if (kp) {
+      int pos = off + __popc(m & ((1u << lane) - 1));
+      if (pos < cap) {
+        xy[2 * (size_t)pos] = (float)x;
+        xy[2 * (size_t)pos + 1] = (float)y;
+        score[pos] = v;
+      }
+    }
+    off += __popc(m);
+  }
+}
+
+// convDb (1x1, 256 -> 256) + L2 normalise over channels (superpoint.py:191-192). block = 256 threads (one per
+// output channel), 8 cells.
+constexpr int DB_CELLS = 8;
+__global__ void __launch_bounds__(256) k_head_desc(const float* __restrict__ cda, const float* __restrict__ wt /*[256][256]*/,
+                                                    const float* __restrict__ bias, float* __restrict__ dense, int ncell) {
+  __shared__ float xs[DB_CELLS][256];
+  __shared__ float red[DB_CELLS][8];
+  const int t = threadIdx.x;
+  const int cell0 = blockIdx.x * DB_CELLS;
+  for (int c = 0; c < DB_CELLS; ++c) xs[c][t] = (cell0 + c < ncell) ? cda[(size_t)(cell0 + c) * 256 + t] : 0.f;
+  __syncthreads();
+  float acc[DB_CELLS];
+  const float b = bias[t];
+#pragma unroll
+  for (int c = 0; c < DB_CELLS; ++c) acc[c] = b;
+  for (int k = 0; k < 256; ++k) {
+    float w = wt[k * 256 + t];
+#pragma unroll
+    for (int c = 0; c < DB_CELLS; ++c) acc[c] = fmaf(xs[c][k], w, acc[c]);
+  }
+  const int warp = t >> 5, lane = t & 31;
+#pragma unroll
+  for (int c = 0; c < DB_CELLS; ++c) {
+    float s = warp_sum(acc[c] * acc[c]);
+    if (lane == 0) red[c][warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < DB_CELLS; ++c) {
+    float ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ss += red[c][w];
+    float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    if (cell0 + c < ncell) dense[(size_t)(cell0 + c) * 256 + t] = acc[c] / nrm;
+  }
+}
+
+// sample_descriptors (superpoint.py:80-92) with align_corners=True, zero padding, then per-keypoint L2 normalise.
+// one warp per keypoint; each lane owns 8 channels (2 x float4).
+__global__ void __launch_bounds__(256) k_sample_desc(const float* __restrict__ dense, int Hc, int Wc,
+                                                      const float* __restrict__ xy, int n, float* __restrict__ out) {
+  int kp = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (kp >= n) return;
+  float x = xy[2 * (size_t)kp], y = xy[2 * (size_t)kp + 1];
+  // keypoints - s/2 + 0.5 ; / (w*s - s/2 - 0.5) ; *2 - 1 ; grid_sample unnormalise ((g + 1) / 2) * (size - 1)
+  float gx = ((x - 4.0f) + 0.5f) / (float)(Wc * 8 - 4 - 0.5);
+  float gy = ((y - 4.0f) + 0.5f) / (float)(Hc * 8 - 4 - 0.5);
+  gx = gx * 2.0f - 1.0f;
+  gy = gy * 2.0f - 1.0f;
+  float ix = ((gx + 1.0f) / 2.0f) * (float)(Wc - 1);
+  float iy = ((gy + 1.0f) / 2.0f) * (float)(Hc - 1);
+  float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy;
+  float wx1 = ix - fx, wy1 = iy - fy;
+  float wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy;
+  float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
+  int cxs[4] = {x0, x0 + 1, x0, x0 + 1};
+  int cys[4] = {y0, y0, y0 + 1, y0 + 1};
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (cxs[q] >= 0 && cxs[q] < Wc && cys[q] >= 0 && cys[q] < Hc) {
+      const float4* p = reinterpret_cast<const float4*>(dense + ((size_t)cys[q] * Wc + cxs[q]) * 256);
+      float4 a = p[lane], b = p[lane + 32];
+      v[0] = fmaf(a.x, wgt[q], v[0]);
+      v[1] = fmaf(a.y, wgt[q], v[1]);
+      v[2] = fmaf(a.z, wgt[q], v[2]);
+      v[3] = fmaf(a.w, wgt[q], v[3]);
+      v[4] = fmaf(b.x, wgt[q], v[4]);
+      v[5] = fmaf(b.y, wgt[q], v[5]);
+      v[6] = fmaf(b.z, wgt[q], v[6]);
+      v[7] = fmaf(b.w, wgt[q], v[7]);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ss = fmaf(v[c], v[c], ss);
+  ss = warp_sum(ss);
+  float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  float4* o = reinterpret_cast<float4*>(out + (size_t)kp * 256);
+  o[lane] = make_float4(v[0] / nrm, v[1] / nrm, v[2] / nrm, v[3] / nrm);
+  o[lane + 32] = make_float4(v[4] / nrm, v[5] / nrm, v[6] / nrm, v[7] / nrm);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+
+static int sp_conv3x3(b2_context* ctx, cudaStream_t st, const float* in, int li, float* out, int H, int W, bool pool) {
+  SuperPointState* s = ctx->sp;
+  dim3 grid(cdiv(W, CT_W), cdiv(H, CT_H), SP_CO[li] / 64);
+  if (pool)
+    B2_LAUNCH(ctx, k_conv3x3<1>, grid, 256, 0, st, in, s->w[li], s->b[li], out, H, W, SP_CI[li], SP_CO[li]);
+  else
+    B2_LAUNCH(ctx, k_conv3x3<0>, grid, 256, 0, st, in, s->w[li], s->b[li], out, H, W, SP_CI[li], SP_CO[li]);
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+
+static size_t nms_smem_bytes() { return (size_t)NREG * 4 * sizeof(float) + (size_t)NREG * 3; }
+
+extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, size_t n_floats) {
+  if (!ctx || !blob) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_floats != SP_NFLOATS)
+    return b2_fail(ctx, B2_ERR_ARG, "superpoint blob must hold 1300865 floats, got " + std::to_string(n_floats));
+  cudaSetDevice(ctx->device);
+  if (!ctx->sp) ctx->sp = new SuperPointState();
+  SuperPointState* s = ctx->sp;
+  // repack on host: 3x3 OIHW -> [tap][cin][cout]; 1x1 OI -> [cin][cout]
+  std::vector<float> packed(SP_NFLOATS);
+  size_t src = 0, dst = 0;
+  size_t woff[SP_NCONV], boff[SP_NCONV];
+  for (int l = 0; l < SP_NCONV; ++l) {
+    const int co = SP_CO[l], ci = SP_CI[l], kk = SP_K[l] * SP_K[l];
+    const float* w = blob + src;
+    woff[l] = dst;
+    for (int o = 0; o < co; ++o)
+      for (int i = 0; i < ci; ++i)
+        for (int tp = 0; tp < kk; ++tp) packed[dst + ((size_t)tp * ci + i) * co + o] = w[((size_t)o * ci + i) * kk + tp];
+    src += (size_t)co * ci * kk;
+    dst += (size_t)co * ci * kk;
+    boff[l] = dst;
+    for (int o = 0; o < co; ++o) packed[dst + o] = blob[src + o];
+    src += co;
+    dst += co;
+    // keep every tensor 16-byte aligned for float4 loads: all sizes are multiples of 4 except convPb (65 outputs)
+  }
+  // alignment: lay tensors out individually aligned to 256 B on the device
+  size_t total = 0;
+  size_t dwoff[SP_NCONV], dboff[SP_NCONV];
+  for (int l = 0; l < SP_NCONV; ++l) {
+    size_t nw = (size_t)SP_CO[l] * SP_CI[l] * SP_K[l] * SP_K[l];
+    dwoff[l] = total;
+    total += (nw + 63) / 64 * 64;
+    dboff[l] = total;
+    total += ((size_t)SP_CO[l] + 63) / 64 * 64;
+  }
+  B2_CUDA(ctx, s->wblob.ensure(total * sizeof(float)));
+  for (int l = 0; l < SP_NCONV; ++l) {
+    size_t nw = (size_t)SP_CO[l] * SP_CI[l] * SP_K[l] * SP_K[l];
+    s->w[l] = s->wblob.as<float>() + dwoff[l];
+    s->b[l] = s->wblob.as<float>() + dboff[l];
+    B2_CUDA(ctx, cudaMemcpy(s->w[l], packed.data() + woff[l], nw * sizeof(float), cudaMemcpyHostToDevice));
+    B2_CUDA(ctx, cudaMemcpy(s->b[l], packed.data() + boff[l], SP_CO[l] * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
+  s->loaded = true;
+  return B2_OK;
+}
+
+static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, int channels, size_t pitch, float thr,
+                          int nms_radius, int border, float* out_xy, float* out_score, int cap, int* out_n,
+                          cudaStream_t st) {
+  SuperPointState* s = ctx->sp;
+  if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "superpoint weights not set");
+  if (nms_radius != NR) return b2_fail(ctx, B2_ERR_ARG, "only nms_radius == 4 (the reference default) is built");
+  if (H < 8 || W < 8 || (channels != 1 && channels != 3 && channels != 4)) return b2_fail(ctx, B2_ERR_ARG, "bad image shape");
+  if (border < 0) return b2_fail(ctx, B2_ERR_ARG, "border < 0");
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Hc = H4 / 2, Wc = W4 / 2;
+  const int H8 = Hc * 8, W8 = Wc * 8;
+  s->H = H, s->W = W, s->Hc = Hc, s->Wc = Wc;
+  s->have_dense = false;
+  const size_t px = (size_t)H * W;
+  B2_CUDA(ctx, s->gray.ensure(px));
+  B2_CUDA(ctx, s->a0.ensure(px * 64 * sizeof(float)));
+  B2_CUDA(ctx, s->a1.ensure((size_t)H2 * W2 * 64 * sizeof(float)));
+  B2_CUDA(ctx, s->feat.ensure((size_t)Hc * Wc * 128 * sizeof(float)));
+  B2_CUDA(ctx, s->head.ensure((size_t)Hc * Wc * 256 * sizeof(float)));
+  B2_CUDA(ctx, s->heat.ensure((size_t)H8 * W8 * sizeof(float)));
+  B2_CUDA(ctx, s->nms.ensure((size_t)H8 * W8 * sizeof(float)));
+  B2_CUDA(ctx, s->rowcnt.ensure((size_t)(H8 + 1) * sizeof(int)));
+  B2_CUDA(ctx, s->rowoff.ensure((size_t)(H8 + 2) * sizeof(int)));
+  B2_CUDA(ctx, s->dense.ensure((size_t)Hc * Wc * 256 * sizeof(float)));
+  float* a0 = s->a0.as<float>();
+  float* a1 = s->a1.as<float>();
+  float* feat = s->feat.as<float>();
+  float* head = s->head.as<float>();
+
+  B2_LAUNCH(ctx, k_to_gray, dim3(cdiv(W, 256), H), 256, 0, st, image, pitch, channels, H, W, s->gray.as<uint8_t>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W);
+  B2_CHECK_LAUNCH(ctx);
+  int rc;
+  // encoder (superpoint.py:148-158); pools fused into conv1b / conv2b / conv3b
+  if ((rc = sp_conv3x3(ctx, st, a0, 1, a1, H, W, true))) return rc;      // conv1b + pool -> (H2, W2, 64) in a1
+  if ((rc = sp_conv3x3(ctx, st, a1, 2, a0, H2, W2, false))) return rc;   // conv2a
+  if ((rc = sp_conv3x3(ctx, st, a0, 3, a1, H2, W2, true))) return rc;    // conv2b + pool -> (H4, W4, 64)
+  if ((rc = sp_conv3x3(ctx, st, a1, 4, a0, H4, W4, false))) return rc;   // conv3a -> 128
+  if ((rc = sp_conv3x3(ctx, st, a0, 5, a1, H4, W4, true))) return rc;    // conv3b + pool -> (Hc, Wc, 128)
+  if ((rc = sp_conv3x3(ctx, st, a1, 6, a0, Hc, Wc, false))) return rc;   // conv4a
+  if ((rc = sp_conv3x3(ctx, st, a0, 7, feat, Hc, Wc, false))) return rc; // conv4b
+  // detector head (superpoint.py:161-167)
+  if ((rc = sp_conv3x3(ctx, st, feat, 8, head, Hc, Wc, false))) return rc;  // convPa
+  B2_LAUNCH(ctx, k_head_scores, cdiv(Hc * Wc, PB_CELLS), 128, 0, st, head, s->w[9], s->b[9], s->heat.as<float>(), Hc, Wc);
+  B2_CHECK_LAUNCH(ctx);
+  B2_CUDA(ctx, cudaMemsetAsync(s->rowcnt.p, 0, (size_t)(H8 + 1) * sizeof(int), st));
+  B2_LAUNCH(ctx, k_nms, dim3(cdiv(W8, NT_W), cdiv(H8, NT_H)), 256, nms_smem_bytes(), st, s->heat.as<float>(),
+            s->nms.as<float>(), H8, W8, thr, border, s->rowcnt.as<int>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_scan_rows, 1, 1024, 0, st, s->rowcnt.as<int>(), s->rowoff.as<int>(), H8);
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_compact, cdiv(H8, 8), 256, 0, st, s->nms.as<float>(), H8, W8, thr, border, s->rowoff.as<int>(), out_xy,
+            out_score, cap);
+  B2_CHECK_LAUNCH(ctx);
+  // descriptor head (superpoint.py:190-192): dense map stays resident for the describe stage
+  if ((rc = sp_conv3x3(ctx, st, feat, 10, head, Hc, Wc, false))) return rc;  // convDa
+  B2_LAUNCH(ctx, k_head_desc, cdiv(Hc * Wc, DB_CELLS), 256, 0, st, head, s->w[11], s->b[11], s->dense.as<float>(), Hc * Wc);
+  B2_CHECK_LAUNCH(ctx);
+  int n = 0;
+  B2_CUDA(ctx, cudaMemcpyAsync(&n, s->rowoff.as<int>() + H8, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  s->n_kp = n;
+  s->have_dense = true;
+  *out_n = n;
+  ctx->debug["heat"] = {s->heat.as<float>(), (int64_t)H8 * W8};
+  ctx->debug["nms"] = {s->nms.as<float>(), (int64_t)H8 * W8};
+  ctx->debug["dense_desc"] = {s->dense.as<float>(), (int64_t)Hc * Wc * 256};
+  ctx->debug["conv4b"] = {feat, (int64_t)Hc * Wc * 128};
+  return B2_OK;
+}
+
+extern "C" int b2_superpoint_detect_dev(b2_context* ctx, const uint8_t* image, int H, int W, int channels, size_t pitch,
+                                        float thr, int nms_radius, int border, float* out_xy, float* out_score, int cap,
+                                        int* out_n, void* stream) {
+  if (!ctx || !image || !out_xy || !out_score || !out_n || cap < 0) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return sp_detect_impl(ctx, image, H, W, channels, pitch, thr, nms_radius, border, out_xy, out_score, cap, out_n,
+                        (cudaStream_t)stream);
+}
+
+static int sp_describe_impl(b2_context* ctx, const float* xy, int n, float* out_desc, cudaStream_t st) {
+  SuperPointState* s = ctx->sp;
+  if (!s || !s->have_dense) return b2_fail(ctx, B2_ERR_STATE, "describe called before a successful detect");
+  if (n == 0) return B2_OK;
+  B2_LAUNCH(ctx, k_sample_desc, cdiv(n, 8), 256, 0, st, s->dense.as<float>(), s->Hc, s->Wc, xy, n, out_desc);
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+
+extern "C" int b2_superpoint_describe_dev(b2_context* ctx, const float* xy, int n, float* out_desc, void* stream) {
+  if (!ctx || n < 0 || (n > 0 && (!xy || !out_desc))) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return sp_describe_impl(ctx, xy, n, out_desc, (cudaStream_t)stream);
+}
+
+extern "C" int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, int H, int W, int channels, float thr,
+                                         int nms_radius, int border, float* out_xy, float* out_score, int cap,
+                                         int* out_n) {
+  if (!ctx || !image || !out_xy || !out_score || !out_n || cap < 0) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t bytes = (size_t)H * W * channels;
+  B2_CUDA(ctx, ctx->stage_d[0].ensure(bytes));
+  B2_CUDA(ctx, ctx->stage_d[1].ensure((size_t)cap * 2 * sizeof(float) + 16));
+  B2_CUDA(ctx, ctx->stage_d[2].ensure((size_t)cap * sizeof(float) + 16));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[0].p, image, bytes, cudaMemcpyHostToDevice, st));
+  int rc = sp_detect_impl(ctx, ctx->stage_d[0].as<uint8_t>(), H, W, channels, (size_t)W * channels, thr, nms_radius, border,
+                          ctx->stage_d[1].as<float>(), ctx->stage_d[2].as<float>(), cap, out_n, st);
+  if (rc) return rc;
+  int n = *out_n < cap ? *out_n : cap;
+  if (n > 0) {
+    B2_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->stage_d[1].p, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->stage_d[2].p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int n, float* out_desc) {
+  if (!ctx || n < 0 || (n > 0 && (!xy || !out_desc))) return B2_ERR_ARG;
+  if (n == 0) return B2_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  B2_CUDA(ctx, ctx->stage_d[3].ensure((size_t)n * 2 * sizeof(float)));
+  B2_CUDA(ctx, ctx->stage_d[4].ensure((size_t)n * 256 * sizeof(float)));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[3].p, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = sp_describe_impl(ctx, ctx->stage_d[3].as<float>(), n, ctx->stage_d[4].as<float>(), st);
+  if (rc) return rc;
+  B2_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->stage_d[4].p, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  return B2_OK;
+}

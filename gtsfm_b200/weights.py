@@ -1,0 +1,117 @@
+"""Host-side weight handling: reference checkpoints (state dicts) -> packed fp32 blobs for the C ABI.
+
+The C library takes each model as ONE contiguous float32 blob in a fixed, documented tensor order; the tensors keep
+the checkpoint's own layouts (Conv2d OIHW, nn.Linear (out, in), Conv1d (out, in, 1)) and the library repacks on upload.
+Checkpoint names / shapes are the reference's:
+  * SuperPoint : thirdparty/SuperGluePretrainedNetwork/models/superpoint.py:119-134
+  * LightGlue  : thirdparty/LightGlue/lightglue/lightglue.py:393-408 (+ legacy key rename :424-430)
+  * SuperGlue  : thirdparty/SuperGluePretrainedNetwork/models/superglue.py:195-224 (eval BatchNorm folded here)
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Dict, List, Union
+
+import numpy as np
+
+SUPERPOINT_LAYERS = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b",
+                     "convPa", "convPb", "convDa", "convDb"]
+SUPERPOINT_ORDER: List[str] = [f"{n}.{p}" for n in SUPERPOINT_LAYERS for p in ("weight", "bias")]
+
+LIGHTGLUE_LAYERS = 9
+
+
+def _lg_layer(i: int) -> List[str]:
+    s, c = f"transformers.{i}.self_attn.", f"transformers.{i}.cross_attn."
+    names = []
+    for p in ("Wqkv", "out_proj", "ffn.0", "ffn.1", "ffn.3"):
+        names += [s + p + ".weight", s + p + ".bias"]
+    for p in ("to_qk", "to_v", "to_out", "ffn.0", "ffn.1", "ffn.3"):
+        names += [c + p + ".weight", c + p + ".bias"]
+    return names
+
+
+LIGHTGLUE_ORDER: List[str] = (
+    ["posenc.Wr.weight"]
+    + [n for i in range(LIGHTGLUE_LAYERS) for n in _lg_layer(i)]
+    + [n for i in range(LIGHTGLUE_LAYERS) for n in (f"log_assignment.{i}.matchability.weight", f"log_assignment.{i}.matchability.bias",
+                                                    f"log_assignment.{i}.final_proj.weight", f"log_assignment.{i}.final_proj.bias")]
+    + [n for i in range(LIGHTGLUE_LAYERS - 1) for n in (f"token_confidence.{i}.token.0.weight", f"token_confidence.{i}.token.0.bias")]
+)
+
+SUPERGLUE_GNN_LAYERS = 18
+# after BN folding: kenc conv 0,3,6,9,12 ; per GNN layer q,k,v,merge,mlp0,mlp3 ; final_proj ; bin_score
+SUPERGLUE_ORDER: List[str] = (
+    [f"kenc.encoder.{i}.{p}" for i in (0, 3, 6, 9, 12) for p in ("weight", "bias")]
+    + [f"gnn.layers.{l}.{m}.{p}" for l in range(SUPERGLUE_GNN_LAYERS)
+       for m in ("attn.proj.0", "attn.proj.1", "attn.proj.2", "attn.merge", "mlp.0", "mlp.3") for p in ("weight", "bias")]
+    + ["final_proj.weight", "final_proj.bias", "bin_score"]
+)
+
+StateDict = Dict[str, np.ndarray]
+
+
+def load_state_dict(src: Union[str, Path, StateDict]) -> StateDict:
+    """A checkpoint path (torch.save of name -> tensor, like the reference's .pth files) or an in-memory dict."""
+    if isinstance(src, dict):
+        return {k: np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v) for k, v in src.items()}
+    path = Path(src)
+    if not path.exists():
+        raise FileNotFoundError(f"weights not found at {path}")
+    import torch
+
+    sd = torch.load(str(path), map_location="cpu")
+    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def _pack(sd: StateDict, order: List[str]) -> np.ndarray:
+    missing = [k for k in order if k not in sd]
+    if missing:
+        raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
+    return np.concatenate([np.asarray(sd[k], np.float32).ravel() for k in order]).astype(np.float32)
+
+
+def pack_superpoint(sd: StateDict) -> np.ndarray:
+    blob = _pack(sd, SUPERPOINT_ORDER)
+    assert blob.size == 1300865, blob.size
+    return blob
+
+
+def pack_lightglue(sd: StateDict) -> np.ndarray:
+    sd = dict(sd)
+    for i in range(LIGHTGLUE_LAYERS):  # legacy checkpoint keys, lightglue.py:424-430
+        for old, new in ((f"self_attn.{i}", f"transformers.{i}.self_attn"), (f"cross_attn.{i}", f"transformers.{i}.cross_attn")):
+            for k in list(sd):
+                if k.startswith(old + "."):
+                    sd[k.replace(old, new, 1)] = sd.pop(k)
+    return _pack(sd, LIGHTGLUE_ORDER)
+
+
+def fold_superglue_batchnorm(sd: StateDict, eps: float = 1e-5) -> StateDict:
+    """eval-mode BatchNorm1d folded into the preceding k=1 Conv1d: w' = w * g / sqrt(var + eps), b' = (b - mu) * g / sqrt(var + eps) + beta."""
+    out: StateDict = {}
+    pairs = [(f"kenc.encoder.{i}", f"kenc.encoder.{i + 1}") for i in (0, 3, 6, 9)]
+    pairs += [(f"gnn.layers.{l}.mlp.0", f"gnn.layers.{l}.mlp.1") for l in range(SUPERGLUE_GNN_LAYERS)]
+    folded = set()
+    for conv, bn in pairs:
+        w = np.asarray(sd[conv + ".weight"], np.float64)[:, :, 0]
+        b = np.asarray(sd[conv + ".bias"], np.float64)
+        g = np.asarray(sd[bn + ".weight"], np.float64)
+        beta = np.asarray(sd[bn + ".bias"], np.float64)
+        mu = np.asarray(sd[bn + ".running_mean"], np.float64)
+        var = np.asarray(sd[bn + ".running_var"], np.float64)
+        scale = g / np.sqrt(var + eps)
+        out[conv + ".weight"] = (w * scale[:, None]).astype(np.float32)
+        out[conv + ".bias"] = ((b - mu) * scale + beta).astype(np.float32)
+        folded.add(conv)
+    for k, v in sd.items():
+        base = k.rsplit(".", 1)[0]
+        if base in folded or k in out:
+            continue
+        a = np.asarray(v)
+        out[k] = a[:, :, 0].astype(np.float32) if (a.ndim == 3 and a.shape[2] == 1) else a
+    return out
+
+
+def pack_superglue(sd: StateDict) -> np.ndarray:
+    return _pack(fold_superglue_batchnorm(sd), SUPERGLUE_ORDER)

@@ -1,0 +1,137 @@
+/*
+ * gtsfm_b200 — C ABI of the B200-native pairwise deep front-end (SuperPoint -> LightGlue/SuperGlue -> RANSAC).
+ *
+ * This is the drop-in boundary.  Every entry point is plain C: opaque handle, raw pointers, sizes,
+ * an `int` status (0 = ok, <0 = error; text via b2_last_error).  No torch / C++ types cross it.  `*_dev` entry points
+ * take DEVICE pointers plus a CUDA stream (passed as void*, i.e. a cudaStream_t / CUstream; NULL = legacy default
+ * stream) so PyTorch tensors go in and out through `tensor.data_ptr()`; the `*_host` entry points take HOST pointers
+ * and do the H2D / D2H copies themselves (this is what the per-call GTSfM plugins use, mirroring the reference's
+ * `.to(device)` / `.cpu().numpy()` inside each call).
+ *
+ * Reference interface each group replaces (paths relative to the reference repo):
+ *   b2_superpoint_*  : gtsfm/frontend/detector_descriptor/superpoint.py:63-93 (detect_and_describe) and the model
+ *                      thirdparty/SuperGluePretrainedNetwork/models/superpoint.py:145-202
+ *   b2_lightglue_*   : gtsfm/frontend/matcher/lightglue_matcher.py:43-112 and
+ *                      thirdparty/LightGlue/lightglue/lightglue.py:474-629
+ *   b2_superglue_*   : gtsfm/frontend/matcher/superglue_matcher.py:47-115 and
+ *                      thirdparty/SuperGluePretrainedNetwork/models/superglue.py:226-283
+ *   b2_ransac_*      : gtsfm/frontend/verifier/ransac.py:52-111 (cv2.findEssentialMat / findFundamentalMat) and
+ *                      gtsfm/utils/verification.py:54-96 (cv2.recoverPose)
+ *
+ * Threading: a handle serialises its own calls with an internal mutex (Dask workers run one thread per process,
+ * gtsfm/runner.py:153-155); use one handle per thread/stream for concurrency.
+ */
+#ifndef GTSFM_B200_H
+#define GTSFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_context b2_context;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------------------- */
+int b2_version(void);
+/* Creates a context on CUDA device `device`.  Fails (returns <0, *out = NULL) when no sm_100 device is present. */
+int b2_create(int device, b2_context** out);
+void b2_destroy(b2_context* ctx);
+const char* b2_last_error(const b2_context* ctx);
+/* Number of kernels this library has launched through `ctx` since creation (bench.py's "gpu_launches"). */
+uint64_t b2_launch_count(const b2_context* ctx);
+/* Copies a named intermediate device buffer of the last call to host (tests only). Returns #floats written or <0. */
+int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host_out, int64_t max_floats);
+
+/* ---- SuperPoint -------------------------------------------------------------------------------------------------- */
+/* `blob`: the 24 state-dict tensors in reference order (conv1a.weight, conv1a.bias, conv1b.weight, ... convDb.bias;
+ * SURVEY.md Appendix A), OIHW fp32, concatenated.  n_floats must equal 1300865. */
+int b2_superpoint_set_weights(b2_context* ctx, const float* host_blob, size_t n_floats);
+
+/* Detect stage on a device image.  `image`: uint8, `channels` in {1,3,4} interleaved (RGB/RGBA are converted with
+ * cv2's fixed-point COLOR_RGB2GRAY), row pitch in bytes.  Runs encoder + both heads + NMS + threshold + border
+ * removal + ordered compaction.  Keypoints come out in row-major (y, then x) order like torch.nonzero.
+ * out_xy: [cap][2] float (x, y); out_score: [cap] float; *out_n (HOST int) = number found (may exceed cap: only the
+ * first cap are written).  Synchronises `stream` before returning (the count is data dependent). */
+int b2_superpoint_detect_dev(b2_context* ctx, const uint8_t* image, int height, int width, int channels, size_t pitch,
+                             float keypoint_threshold, int nms_radius, int border, float* out_xy, float* out_score,
+                             int cap, int* out_n, void* stream);
+/* Describe stage: bilinear-samples the dense descriptor map of the LAST detect call at `n` (x, y) positions and
+ * L2-normalises.  out_desc: [n][256] float row-major.  Asynchronous on `stream`. */
+int b2_superpoint_describe_dev(b2_context* ctx, const float* xy, int n, float* out_desc, void* stream);
+/* Device top-k by score (k largest, ties broken by lower index), result kept in row-major order; writes the selected
+ * indices (int32, ascending) and returns count in *out_k (HOST).  For the batched path; the per-call plugin uses the
+ * reference's host argpartition to keep its index order. */
+int b2_topk_indices_dev(b2_context* ctx, const float* scores, int n, int k, int32_t* out_idx, int* out_k, void* stream);
+
+/* Host-pointer variants (H2D / D2H inside). */
+int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, int height, int width, int channels,
+                              float keypoint_threshold, int nms_radius, int border, float* out_xy, float* out_score,
+                              int cap, int* out_n);
+int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int n, float* out_desc);
+
+/* ---- LightGlue --------------------------------------------------------------------------------------------------- */
+/* `blob`: packed fp32 tensors in the order documented in gtsfm_b200/weights.py::LIGHTGLUE_ORDER (nn.Linear layout
+ * (out,in) row-major as in the checkpoint).  n_floats must equal 11851601 (the 251 parameter tensors; the
+ * confidence_thresholds buffer is recomputed). */
+int b2_lightglue_set_weights(b2_context* ctx, const float* host_blob, size_t n_floats);
+
+typedef struct b2_lightglue_params {
+  float depth_confidence;  /* 0.95; <= 0 disables early exit   (lightglue.py:330)            */
+  float width_confidence;  /* 0.99; <= 0 disables pruning      (lightglue.py:331)            */
+  float filter_threshold;  /* 0.1                              (lightglue.py:332)            */
+  int prune_min_kpts;      /* -1 = reference CPU semantics (prune at every layer); 1536 = its CUDA+flash value */
+} b2_lightglue_params;
+
+/* kp: [n][2] float (x, y) pixels; desc: [n][256] float.  out_matches: [min(n0,n1)][2] int64 rows (idx0, idx1)
+ * ascending in idx0; out_scores: [min(n0,n1)] float (exp of the log assignment) or NULL.  *out_k, *out_stop_layer are
+ * HOST ints (stop layer is 1-based like the reference's "stop").  Synchronises `stream`. */
+int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
+                           const float* desc1, int n1, const b2_lightglue_params* params, int64_t* out_matches,
+                           float* out_scores, int* out_k, int* out_stop_layer, void* stream);
+int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
+                            const float* desc1, int n1, const b2_lightglue_params* params, int64_t* out_matches,
+                            float* out_scores, int* out_k, int* out_stop_layer);
+
+/* ---- SuperGlue --------------------------------------------------------------------------------------------------- */
+/* `blob`: packed fp32 tensors in gtsfm_b200/weights.py::SUPERGLUE_ORDER with eval-mode BatchNorm already folded
+ * into the preceding Conv1d by the host loader. */
+int b2_superglue_set_weights(b2_context* ctx, const float* host_blob, size_t n_floats);
+/* score: [n] keypoint responses; (h, w): image sizes used for keypoint normalisation (superglue.py:63-70).
+ * out_matches: [min(n0,n1)][2] uint32 rows (i, matches0[i]) ascending in i. */
+int b2_superglue_match_dev(b2_context* ctx, const float* kp0, const float* score0, const float* desc0, int n0, int h0,
+                           int w0, const float* kp1, const float* score1, const float* desc1, int n1, int h1, int w1,
+                           int sinkhorn_iters, float match_threshold, uint32_t* out_matches, float* out_scores,
+                           int* out_k, void* stream);
+int b2_superglue_match_host(b2_context* ctx, const float* kp0, const float* score0, const float* desc0, int n0, int h0,
+                            int w0, const float* kp1, const float* score1, const float* desc1, int n1, int h1, int w1,
+                            int sinkhorn_iters, float match_threshold, uint32_t* out_matches, float* out_scores,
+                            int* out_k);
+
+/* ---- RANSAC verifier --------------------------------------------------------------------------------------------- */
+typedef struct b2_ransac_params {
+  double threshold;   /* inlier threshold: max point-to-epipolar-line style distance (same unit as the points):      */
+                      /* thr_px / fx for E on normalised points, thr_px for F on pixels (ransac.py:79,107)           */
+  double confidence;  /* 0.999999 (ransac.py:22)                                                                     */
+  int max_iters;      /* hypothesis budget: E 1000 (cv2 default, ransac.py:74-81) ; F capped by the library at 4096  */
+  uint64_t seed;      /* fixed per call => run-to-run identical results (repro test)           */
+} b2_ransac_params;
+
+/* x1, x2: [k][2] double matched points (normalised coordinates for E, pixels for F).
+ * out_model: 9 doubles row-major (E or F, x2^T M x1 = 0); out_mask: [k] uint8; *out_num_inliers HOST int.
+ * For E also recovers the pose by the cheirality vote (cv2.recoverPose semantics): out_R 9 doubles row-major (i2Ri1),
+ * out_t 3 doubles (unit i2ti1); may be NULL.  Returns 1 when no model could be estimated (mask all zero). */
+int b2_ransac_essential_host(b2_context* ctx, const double* x1, const double* x2, int k, const b2_ransac_params* params,
+                             double* out_model, uint8_t* out_mask, int* out_num_inliers, double* out_R, double* out_t);
+int b2_ransac_fundamental_host(b2_context* ctx, const double* x1, const double* x2, int k,
+                               const b2_ransac_params* params, double* out_model, uint8_t* out_mask,
+                               int* out_num_inliers);
+/* cv2.recoverPose restated: decompose E, pick (R, t) with most points in front of both cameras. */
+int b2_recover_pose_host(b2_context* ctx, const double* E, const double* x1, const double* x2, int k, double* out_R,
+                         double* out_t, int* out_num_good);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTSFM_B200_H */

@@ -1,0 +1,61 @@
+"""CPU suite: the oracle restatement against the committed golden vectors (written by the unmodified reference)."""
+import numpy as np
+import pytest
+
+from gtsfm_b200 import synthetic as syn
+from oracle import lightglue_ref, superglue_ref, superpoint_ref, verifier_ref
+
+
+@pytest.mark.parametrize("name,frame", [("tiny", (0, 120, 160)), ("odd", (3, 203, 317))])
+def test_superpoint_oracle_vs_golden(golden_dir, name, frame):
+    fx = np.load(golden_dir / f"superpoint_{name}.npz")
+    gray = superpoint_ref.rgb_to_gray_u8(syn.synthetic_frame(*frame))
+    kp, sc, desc = superpoint_ref.superpoint_forward(gray.astype(np.float32) / 255.0, syn.superpoint_state_dict(0))
+    assert np.array_equal(kp, fx["keypoints"].astype(np.float32))
+    np.testing.assert_allclose(sc, fx["scores"], atol=1e-6)
+    assert np.abs(desc[fx["desc_rows"]] - fx["desc"]).max() < 1e-5
+
+
+def test_gray_conversion_matches_cv2():
+    import cv2
+
+    rgb = syn.synthetic_frame(11, 64, 96)
+    assert np.array_equal(superpoint_ref.rgb_to_gray_u8(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+
+
+@pytest.mark.parametrize("tag", ["full_5", "prune_7", "stop_8", "prune_9"])
+def test_lightglue_oracle_vs_golden(golden_dir, tag):
+    fx = np.load(golden_dir / f"lightglue_{tag}.npz")
+    kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
+    tr = {}
+    m = lightglue_ref.lightglue_match(kp0, d0, kp1, d1, syn.lightglue_state_dict(2, str(fx["profile"])), trace=tr)
+    assert np.array_equal(m, fx["matches"]) and tr["stop"] == int(fx["stop"])
+    assert np.array_equal(tr["sizes"], fx["sizes"])
+
+
+@pytest.mark.parametrize("seed", [5, 9])
+def test_superglue_oracle_vs_golden(golden_dir, seed):
+    fx = np.load(golden_dir / f"superglue_{seed}.npz")
+    kp0, sc0, d0, kp1, sc1, d1, _ = syn.synthetic_features(seed, int(fx["n0"]), int(fx["n1"]))
+    m = superglue_ref.superglue_match(kp0, sc0, d0, kp1, sc1, d1, (480, 640, 3), (480, 640, 3), syn.superglue_state_dict(1))
+    assert m.dtype == np.uint32 and np.array_equal(m, fx["matches"])
+
+
+def test_verifier_oracle_two_planes():
+    """tests/frontend/verifier/test_verifier_base.py:81-100 through the cv2-driven oracle."""
+    uv1, uv2, R, t = verifier_ref.two_planes_scene(4, 4)
+    matches = np.stack([np.arange(8), np.arange(8)], -1).astype(np.uint32)
+    Rc, tc, rows, ratio, _ = verifier_ref.verify_cv2(uv1, uv2, matches, (1.0, 0, 0), (1.0, 0, 0), True, 0.5)
+    assert verifier_ref.rot_angle_deg(R, Rc) < 2 and verifier_ref.dir_angle_deg(t, tc) < 2
+    assert np.array_equal(rows, matches)
+
+
+def test_verifier_oracle_vs_golden(golden_dir):
+    import cv2
+
+    fx = np.load(golden_dir / "verifier_1.npz")
+    kp1, kp2, matches, K, R, t, is_in = verifier_ref.synthetic_two_view(1, 200, 0.5)
+    Rc, tc, rows, ratio, E = verifier_ref.verify_cv2(kp1, kp2, matches, K, K, True, 4.0)
+    assert verifier_ref.rot_angle_deg(R, Rc) < 1.0
+    if cv2.__version__ == str(fx["cv2_version"]):
+        assert np.array_equal(rows, fx["rows_cv"])
