@@ -17,7 +17,7 @@ class B200Error(RuntimeError):
 
 
 class LightGlueParams(C.Structure):
-    _fields_ = [("depth_confidence", C.c_float), ("width_confidence", C.c_float), ("filter_threshold", C.c_float),
+    _fields_ = [("depth_confidence", C.c_double), ("width_confidence", C.c_double), ("filter_threshold", C.c_double),
                 ("prune_min_kpts", C.c_int)]
 
 

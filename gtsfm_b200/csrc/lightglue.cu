@@ -1,0 +1,681 @@
+// LightGlue matcher for sm_100a, as GTSfM drives it (features = "superpoint").
+//
+// Reference semantics restated (paths relative to the reference repo):
+//   thirdparty/LightGlue/lightglue/lightglue.py:31-43 (bbox keypoint normalisation), :68-81 (rotary table),
+//   :140-172 (SelfBlock), :175-230 (CrossBlock, shared-sim branch), :84-94 + :645-656 (confidence / early exit),
+//   :636-643 + :551-566 (pruning), :265-318 (assignment + filter), :474-629 (_forward); wrapper
+//   gtsfm/frontend/matcher/lightglue_matcher.py:43-112.
+//
+// HBM layout: residual streams [N][256] fp32 row-major; attention operands head-major [4][N][64]; rotary table
+// cos/sin [N][32]; the (N0 x N1) similarity of the final assignment is materialised once in fp32.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace {
+constexpr int LG_LAYERS = 9;
+constexpr size_t LG_NFLOATS = 11851601;
+constexpr int D = 256;
+
+struct SelfW {
+  float *wqkv, *bqkv, *wout, *bout, *w0, *b0, *lng, *lnb, *w3, *b3;
+};
+struct CrossW {
+  float *wqk, *bqk, *wv, *bv, *wout, *bout, *w0, *b0, *lng, *lnb, *w3, *b3;
+};
+struct AssignW {
+  float *wm, *bm, *wf, *bf;
+};
+struct ConfW {
+  float *w, *b;
+};
+}  // namespace
+
+struct LgSide {  // per-image workspace
+  DevBuf x[2], qkv, q, k, v, ctx, msg, h, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, amax, aidx;
+  int cur = 0;  // which of x / cs / sn / ind is live
+  int n = 0;
+};
+
+struct LightGlueState {
+  bool loaded = false;
+  DevBuf wblob;
+  float* wr = nullptr;
+  SelfW sw[LG_LAYERS];
+  CrossW cw[LG_LAYERS];
+  AssignW aw[LG_LAYERS];
+  ConfW tw[LG_LAYERS - 1];
+  float thr[LG_LAYERS];
+  LgSide side[2];
+  DevBuf sim, counters, bbox, outm, outs;
+  HostBuf hread;
+};
+
+void lg_destroy(b2_context* ctx) {
+  if (!ctx->lg) return;
+  LightGlueState* s = ctx->lg;
+  s->wblob.release();
+  for (auto& sd : s->side) {
+    DevBuf* bufs[] = {&sd.x[0], &sd.x[1], &sd.qkv, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.cs[0], &sd.cs[1],
+                      &sd.sn[0], &sd.sn[1], &sd.ind[0], &sd.ind[1], &sd.conf, &sd.mat, &sd.src, &sd.md, &sd.rmax,
+                      &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
+    for (DevBuf* b : bufs) b->release();
+  }
+  s->sim.release();
+  s->counters.release();
+  s->bbox.release();
+  s->outm.release();
+  s->outs.release();
+  s->hread.release();
+  delete s;
+  ctx->lg = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+
+// normalize_keypoints with size=None (lightglue.py:31-43) + LearnableFourierPositionalEncoding (:68-81), one block.
+// Also initialises ind[n] = n.
+__global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp, int n, const float* __restrict__ wr /*[32][2]*/,
+                                                     float* __restrict__ cs, float* __restrict__ sn, int* __restrict__ ind) {
+  __shared__ float red[4][32];
+  __shared__ float bb[4];
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float x = kp[2 * i], y = kp[2 * i + 1];
+    mnx = fminf(mnx, x), mny = fminf(mny, y), mxx = fmaxf(mxx, x), mxy = fmaxf(mxy, y);
+  }
+  mnx = -warp_max(-mnx), mny = -warp_max(-mny), mxx = warp_max(mxx), mxy = warp_max(mxy);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[0][warp] = mnx, red[1][warp] = mny, red[2][warp] = mxx, red[3][warp] = mxy;
+  __syncthreads();
+  if (warp == 0) {
+    float a = -warp_max(-red[0][lane]), b = -warp_max(-red[1][lane]), c = warp_max(red[2][lane]), d = warp_max(red[3][lane]);
+    if (lane == 0) bb[0] = a, bb[1] = b, bb[2] = c, bb[3] = d;
+  }
+  __syncthreads();
+  // size = 1 + max - min ; shift = size / 2 ; scale = max(size) / 2
+  const float sx = 1.0f + bb[2] - bb[0], sy = 1.0f + bb[3] - bb[1];
+  const float shx = sx / 2.0f, shy = sy / 2.0f, sc = fmaxf(sx, sy) / 2.0f;
+  for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
+    int p = i >> 5, f = i & 31;
+    float x = (kp[2 * p] - shx) / sc, y = (kp[2 * p + 1] - shy) / sc;
+    float pr = x * wr[2 * f] + y * wr[2 * f + 1];
+    cs[i] = cosf(pr);
+    sn[i] = sinf(pr);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ind[i] = i;
+}
+
+// qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64].
+__global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict__ qkv, const float* __restrict__ cs,
+                                                          const float* __restrict__ sn, int n, float* __restrict__ q,
+                                                          float* __restrict__ k, float* __restrict__ v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n * 4 * 32 pairs
+  if (i >= n * 128) return;
+  int p = i & 31, h = (i >> 5) & 3, r = i >> 7;
+  const float* src = qkv + (size_t)r * 768 + (h * 64 + 2 * p) * 3;
+  float q0 = src[0], k0 = src[1], v0 = src[2], q1 = src[3], k1 = src[4], v1 = src[5];
+  float c = cs[r * 32 + p], s = sn[r * 32 + p];
+  size_t o = ((size_t)h * n + r) * 64 + 2 * p;
+  // (t * cos) + (rotate_half(t) * sin), rotate_half: (x1, x2) -> (-x2, x1)
+  q[o] = __fadd_rn(__fmul_rn(q0, c), __fmul_rn(-q1, s));
+  q[o + 1] = __fadd_rn(__fmul_rn(q1, c), __fmul_rn(q0, s));
+  k[o] = __fadd_rn(__fmul_rn(k0, c), __fmul_rn(-k1, s));
+  k[o + 1] = __fadd_rn(__fmul_rn(k1, c), __fmul_rn(k0, s));
+  v[o] = v0;
+  v[o + 1] = v1;
+}
+
+// LayerNorm(512, eps 1e-5, affine) + exact GELU in place (lightglue.py:152-157). one warp per row.
+__global__ void __launch_bounds__(256) k_lg_ln_gelu(float* __restrict__ h, int n, const float* __restrict__ g,
+                                                     const float* __restrict__ b) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float4* row = reinterpret_cast<float4*>(h + (size_t)r * 512);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = row[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  float mean = warp_sum(s) / 512.0f;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + bq * bq + c * c + d * d;
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) / 512.0f + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c0 = (lane + 32 * i) * 4;
+    float4 gg = *reinterpret_cast<const float4*>(g + c0), bb = *reinterpret_cast<const float4*>(b + c0);
+    float e[4] = {(v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                  (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = 0.5f * e[j] * (1.0f + erff(e[j] * 0.70710678118654752440f));
+    row[lane + 32 * i] = make_float4(e[0], e[1], e[2], e[3]);
+  }
+}
+
+// two per-row heads in one pass: sigmoid(w1.x + b1) and sigmoid(w2.x + b2) (token confidence :84-94, matchability
+// :298-299).  Also raw logit of head 2 when zraw != null.  one warp per row.
+__global__ void __launch_bounds__(256) k_lg_rowheads(const float* __restrict__ x, int n, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, float* __restrict__ o1,
+                                                      float* __restrict__ o2, float* __restrict__ zraw) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float4* row = reinterpret_cast<const float4*>(x + (size_t)r * 256);
+  float4 a = row[lane], b = row[lane + 32];
+  float s1 = 0.f, s2 = 0.f;
+  if (w1) {
+    float4 wa = reinterpret_cast<const float4*>(w1)[lane], wb = reinterpret_cast<const float4*>(w1)[lane + 32];
+    s1 = a.x * wa.x + a.y * wa.y + a.z * wa.z + a.w * wa.w + b.x * wb.x + b.y * wb.y + b.z * wb.z + b.w * wb.w;
+  }
+  if (w2) {
+    float4 wa = reinterpret_cast<const float4*>(w2)[lane], wb = reinterpret_cast<const float4*>(w2)[lane + 32];
+    s2 = a.x * wa.x + a.y * wa.y + a.z * wa.z + a.w * wa.w + b.x * wb.x + b.y * wb.y + b.z * wb.z + b.w * wb.w;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    if (w1) o1[r] = 1.0f / (1.0f + expf(-(s1 + b1[0])));
+    if (w2) {
+      float z = s2 + b2[0];
+      if (o2) o2[r] = 1.0f / (1.0f + expf(-z));
+      if (zraw) zraw[r] = z;
+    }
+  }
+}
+
+// pruning decision + ordered compaction map for one image (single block):
+//   counters[0 + side] += #(conf < thr)            (check_if_stop numerator, lightglue.py:653-655)
+//   keep = matchability > (1 - width_conf) | conf <= thr   (:636-643); src[pos] = old index; counters[2 + side] = #kept
+__global__ void __launch_bounds__(1024) k_lg_prune_plan(const float* __restrict__ conf, const float* __restrict__ mat, int n,
+                                                         float thr, float keep_thr, int side, int* __restrict__ src,
+                                                         int* __restrict__ counters) {
+  __shared__ int wtot[32];
+  __shared__ int carry, unconf;
+  if (threadIdx.x == 0) carry = 0, unconf = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    bool keep = false, unc = false;
+    if (i < n) {
+      float c = conf[i];
+      unc = c < thr;
+      keep = (mat[i] > keep_thr) || (c <= thr);
+    }
+    unsigned km = __ballot_sync(0xffffffffu, keep), um = __ballot_sync(0xffffffffu, unc);
+    if (lane == 0) wtot[warp] = __popc(km);
+    if (lane == 0 && um) atomicAdd(&unconf, __popc(um));
+    __syncthreads();
+    if (warp == 0) {
+      int w = wtot[lane], ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += u;
+      }
+      wtot[lane] = ws - w;
+    }
+    __syncthreads();
+    int pos = carry + wtot[warp] + __popc(km & ((1u << lane) - 1));
+    if (keep) src[pos] = i;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + (keep ? 1 : 0);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counters[side] = unconf;
+    counters[2 + side] = carry;
+  }
+}
+
+// gather rows by src map: x [n][256], cos/sin [n][32], ind [n]  (lightglue.py:556-566)
+__global__ void __launch_bounds__(256) k_lg_gather(const int* __restrict__ src, const int* __restrict__ cnt,
+                                                    const float* __restrict__ x, const float* __restrict__ cs,
+                                                    const float* __restrict__ sn, const int* __restrict__ ind,
+                                                    float* __restrict__ x2, float* __restrict__ cs2, float* __restrict__ sn2,
+                                                    int* __restrict__ ind2) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= *cnt) return;
+  int s = src[r];
+  const float4* a = reinterpret_cast<const float4*>(x + (size_t)s * 256);
+  float4* o = reinterpret_cast<float4*>(x2 + (size_t)r * 256);
+  o[lane] = a[lane];
+  o[lane + 32] = a[lane + 32];
+  cs2[r * 32 + lane] = cs[s * 32 + lane];
+  sn2[r * 32 + lane] = sn[s * 32 + lane];
+  if (lane == 0) ind2[r] = ind[s];
+}
+
+// log-softmax statistics of sim rows: max and log(sum(exp(x - max)))  (F.log_softmax, lightglue.py:271). warp per row.
+__global__ void __launch_bounds__(256) k_lg_row_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ rmax,
+                                                       float* __restrict__ rlog) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= m) return;
+  const float* row = sim + (size_t)r * n;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += expf(row[j] - mx);
+  s = warp_sum(s);
+  if (lane == 0) rmax[r] = mx, rlog[r] = logf(s);
+}
+// same along columns (log_softmax of sim^T, :272): thread per column, coalesced across columns; rows split over
+// blockIdx.y slabs would need a second pass, so one thread walks all rows (m <= 5000).
+__global__ void __launch_bounds__(128) k_lg_col_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ cmax,
+                                                       float* __restrict__ clog) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float mx = -INFINITY;
+  for (int i = 0; i < m; ++i) mx = fmaxf(mx, sim[(size_t)i * n + j]);
+  float s = 0.f;
+  for (int i = 0; i < m; ++i) s += expf(sim[(size_t)i * n + j] - mx);
+  cmax[j] = mx, clog[j] = logf(s);
+}
+
+__device__ __forceinline__ float logsigmoid(float z) {  // F.logsigmoid: min(z, 0) - log1p(exp(-|z|))
+  return fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
+}
+
+// scores[i][j] = (log_softmax_rows + log_softmax_cols) + (logsigmoid(z0_i) + logsigmoid(z1_j))  (:269-274);
+// row arg-max (first maximum) per i. warp per row.
+__global__ void __launch_bounds__(256) k_lg_row_argmax(const float* __restrict__ sim, int m, int n,
+                                                        const float* __restrict__ rmax, const float* __restrict__ rlog,
+                                                        const float* __restrict__ cmax, const float* __restrict__ clog,
+                                                        const float* __restrict__ z0, const float* __restrict__ z1,
+                                                        float* __restrict__ best, int* __restrict__ arg) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= m) return;
+  const float* row = sim + (size_t)r * n;
+  const float rm = rmax[r], rl = rlog[r], l0 = logsigmoid(z0[r]);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < n; j += 32) {
+    float x = row[j];
+    float sc = (((x - rm) - rl) + ((x - cmax[j]) - clog[j])) + (l0 + logsigmoid(z1[j]));
+    if (sc > bv) bv = sc, bi = j;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+  }
+  if (lane == 0) best[r] = bv, arg[r] = bi;
+}
+__global__ void __launch_bounds__(128) k_lg_col_argmax(const float* __restrict__ sim, int m, int n,
+                                                        const float* __restrict__ rmax, const float* __restrict__ rlog,
+                                                        const float* __restrict__ cmax, const float* __restrict__ clog,
+                                                        const float* __restrict__ z0, const float* __restrict__ z1,
+                                                        int* __restrict__ arg) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float cm = cmax[j], cl = clog[j], l1 = logsigmoid(z1[j]);
+  float bv = -INFINITY;
+  int bi = 0;
+  for (int i = 0; i < m; ++i) {
+    float x = sim[(size_t)i * n + j];
+    float sc = (((x - rmax[i]) - rlog[i]) + ((x - cm) - cl)) + (logsigmoid(z0[i]) + l1);
+    if (sc > bv) bv = sc, bi = i;
+  }
+  arg[j] = bi;
+}
+
+// filter_matches (:302-318) + index mapping through ind0 / ind1 (:598-602) + ordered compaction (single block).
+__global__ void __launch_bounds__(1024) k_lg_filter(const float* __restrict__ best0, const int* __restrict__ a0,
+                                                     const int* __restrict__ a1, int m, float th, const int* __restrict__ ind0,
+                                                     const int* __restrict__ ind1, long long* __restrict__ out,
+                                                     float* __restrict__ outs, int* __restrict__ count) {
+  __shared__ int wtot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < m; base += 1024) {
+    int i = base + threadIdx.x;
+    bool valid = false;
+    float ms = 0.f;
+    int j = 0;
+    if (i < m) {
+      j = a0[i];
+      bool mutual = a1[j] == i;
+      ms = mutual ? expf(best0[i]) : 0.f;
+      valid = mutual && ms > th;
+    }
+    unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) wtot[warp] = __popc(vm);
+    __syncthreads();
+    if (warp == 0) {
+      int w = wtot[lane], ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += u;
+      }
+      wtot[lane] = ws - w;
+    }
+    __syncthreads();
+    int pos = carry + wtot[warp] + __popc(vm & ((1u << lane) - 1));
+    if (valid) {
+      out[2 * (size_t)pos] = ind0[i];
+      out[2 * (size_t)pos + 1] = ind1[j];
+      if (outs) outs[pos] = ms;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + (valid ? 1 : 0);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+
+extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size_t n_floats) {
+  if (!ctx || !blob) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_floats != LG_NFLOATS)
+    return b2_fail(ctx, B2_ERR_ARG, "lightglue blob must hold 11851601 floats, got " + std::to_string(n_floats));
+  cudaSetDevice(ctx->device);
+  if (!ctx->lg) ctx->lg = new LightGlueState();
+  LightGlueState* s = ctx->lg;
+  // device copy with every tensor 256-byte aligned
+  std::vector<size_t> sizes;
+  sizes.push_back(64);  // posenc.Wr
+  for (int i = 0; i < LG_LAYERS; ++i) {
+    const size_t self_sz[] = {768 * 256, 768, 256 * 256, 256, 512 * 512, 512, 512, 512, 256 * 512, 256};
+    const size_t cross_sz[] = {256 * 256, 256, 256 * 256, 256, 256 * 256, 256, 512 * 512, 512, 512, 512, 256 * 512, 256};
+    for (size_t z : self_sz) sizes.push_back(z);
+    for (size_t z : cross_sz) sizes.push_back(z);
+  }
+  for (int i = 0; i < LG_LAYERS; ++i) {
+    const size_t asz[] = {256, 1, 256 * 256, 256};
+    for (size_t z : asz) sizes.push_back(z);
+  }
+  for (int i = 0; i < LG_LAYERS - 1; ++i) sizes.push_back(256), sizes.push_back(1);
+  size_t total = 0, src_total = 0;
+  std::vector<size_t> doff;
+  for (size_t z : sizes) {
+    doff.push_back(total);
+    total += (z + 63) / 64 * 64;
+    src_total += z;
+  }
+  if (src_total != LG_NFLOATS) return b2_fail(ctx, B2_ERR_STATE, "internal lightglue layout mismatch");
+  std::vector<float> host(total, 0.f);
+  size_t so = 0;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    memcpy(host.data() + doff[i], blob + so, sizes[i] * sizeof(float));
+    so += sizes[i];
+  }
+  B2_CUDA(ctx, s->wblob.ensure(total * sizeof(float)));
+  B2_CUDA(ctx, cudaMemcpy(s->wblob.p, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  float* base = s->wblob.as<float>();
+  size_t ti = 0;
+  auto next = [&]() { return base + doff[ti++]; };
+  s->wr = next();
+  for (int i = 0; i < LG_LAYERS; ++i) {
+    SelfW& a = s->sw[i];
+    a.wqkv = next(), a.bqkv = next(), a.wout = next(), a.bout = next(), a.w0 = next(), a.b0 = next(), a.lng = next(),
+    a.lnb = next(), a.w3 = next(), a.b3 = next();
+    CrossW& c = s->cw[i];
+    c.wqk = next(), c.bqk = next(), c.wv = next(), c.bv = next(), c.wout = next(), c.bout = next(), c.w0 = next(),
+    c.b0 = next(), c.lng = next(), c.lnb = next(), c.w3 = next(), c.b3 = next();
+  }
+  for (int i = 0; i < LG_LAYERS; ++i) {
+    AssignW& a = s->aw[i];
+    a.wm = next(), a.bm = next(), a.wf = next(), a.bf = next();
+  }
+  for (int i = 0; i < LG_LAYERS - 1; ++i) s->tw[i].w = next(), s->tw[i].b = next();
+  // confidence_threshold buffer (lightglue.py:631-634) evaluated in double then stored as float32 like torch.Tensor([...])
+  for (int i = 0; i < LG_LAYERS; ++i) {
+    double t = 0.8 + 0.1 * exp(-4.0 * i / LG_LAYERS);
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    s->thr[i] = (float)t;
+  }
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+  B2_CUDA(ctx, s->hread.ensure(64));
+  B2_CUDA(ctx, s->counters.ensure(64));
+  s->loaded = true;
+  return B2_OK;
+}
+
+static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  for (int i = 0; i < 2; ++i) {
+    B2_CUDA(ctx, sd.x[i].ensure(N * 256 * 4));
+    B2_CUDA(ctx, sd.cs[i].ensure(N * 32 * 4));
+    B2_CUDA(ctx, sd.sn[i].ensure(N * 32 * 4));
+    B2_CUDA(ctx, sd.ind[i].ensure(N * 4));
+  }
+  B2_CUDA(ctx, sd.qkv.ensure(N * 768 * 4));
+  B2_CUDA(ctx, sd.q.ensure(N * 256 * 4));
+  B2_CUDA(ctx, sd.k.ensure(N * 256 * 4));
+  B2_CUDA(ctx, sd.v.ensure(N * 256 * 4));
+  B2_CUDA(ctx, sd.ctx.ensure(N * 256 * 4));
+  B2_CUDA(ctx, sd.msg.ensure(N * 256 * 4));
+  B2_CUDA(ctx, sd.h.ensure(N * 512 * 4));
+  B2_CUDA(ctx, sd.md.ensure(N * 256 * 4));
+  DevBuf* small[] = {&sd.conf, &sd.mat, &sd.src, &sd.rmax, &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
+  for (DevBuf* b : small) B2_CUDA(ctx, b->ensure(N * 4));
+  sd.cur = 0;
+  sd.n = n;
+  return B2_OK;
+}
+
+// x + ffn(cat[x, msg])  (lightglue.py:152-157,172,228-229): Linear(512,512) -> LN -> GELU -> Linear(512,256) + x
+static int lg_ffn(b2_context* ctx, cudaStream_t st, LgSide& sd, const float* w0, const float* b0, const float* lng,
+                  const float* lnb, const float* w3, const float* b3) {
+  const int n = sd.n;
+  float* x = sd.x[sd.cur].as<float>();
+  GemmArgs g = gemm_linear(x, 256, 256, w0, b0, sd.h.as<float>(), 512, n, 512);
+  g.A2 = sd.msg.as<float>(), g.lda2 = 256, g.K2 = 256, g.ldb = 512;
+  int rc;
+  if ((rc = launch_gemm(ctx, st, g))) return rc;
+  B2_LAUNCH(ctx, k_lg_ln_gelu, cdiv(n, 8), 256, 0, st, sd.h.as<float>(), n, lng, lnb);
+  B2_CHECK_LAUNCH(ctx);
+  GemmArgs g2 = gemm_linear(sd.h.as<float>(), 512, 512, w3, b3, x, 256, n, 256);
+  g2.resid = x, g2.ldr = 256;  // in place: every element is read (as residual) and written by the same thread
+  return launch_gemm(ctx, st, g2);
+}
+
+static int lg_self_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer, LgSide& sd) {
+  const SelfW& w = s->sw[layer];
+  const int n = sd.n;
+  float* x = sd.x[sd.cur].as<float>();
+  int rc;
+  if ((rc = launch_gemm(ctx, st, gemm_linear(x, 256, 256, w.wqkv, w.bqkv, sd.qkv.as<float>(), 768, n, 768)))) return rc;
+  B2_LAUNCH(ctx, k_lg_split_rotary, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
+            sd.sn[sd.cur].as<float>(), n, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>());
+  B2_CHECK_LAUNCH(ctx);
+  if ((rc = launch_flash(ctx, st, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>(), sd.ctx.as<float>(), n, n, 0.125f))) return rc;
+  if ((rc = launch_gemm(ctx, st, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, n, 256)))) return rc;
+  return lg_ffn(ctx, st, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
+}
+
+static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
+  const CrossW& w = s->cw[layer];
+  int rc;
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    float* x = sd.x[sd.cur].as<float>();
+    GemmArgs g = gemm_linear(x, 256, 256, w.wqk, w.bqk, sd.q.as<float>(), 0, sd.n, 256);
+    g.head_major = 1;
+    if ((rc = launch_gemm(ctx, st, g))) return rc;
+    GemmArgs gv = gemm_linear(x, 256, 256, w.wv, w.bv, sd.v.as<float>(), 0, sd.n, 256);
+    gv.head_major = 1;
+    if ((rc = launch_gemm(ctx, st, gv))) return rc;
+  }
+  // m0 = softmax(s * qk0 qk1^T) v1 ; m1 = softmax(s * qk1 qk0^T) v0 with s = 64^-0.5 (the reference scales each
+  // operand by 64^-0.25, lightglue.py:216-221)
+  LgSide &a = s->side[0], &b = s->side[1];
+  if ((rc = launch_flash(ctx, st, a.q.as<float>(), b.q.as<float>(), b.v.as<float>(), a.ctx.as<float>(), a.n, b.n, 0.125f))) return rc;
+  if ((rc = launch_flash(ctx, st, b.q.as<float>(), a.q.as<float>(), a.v.as<float>(), b.ctx.as<float>(), b.n, a.n, 0.125f))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    if ((rc = launch_gemm(ctx, st, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, sd.n, 256)))) return rc;
+    if ((rc = lg_ffn(ctx, st, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3))) return rc;
+  }
+  return B2_OK;
+}
+
+static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
+                         const float* desc1, int n1, const b2_lightglue_params* prm, long long* out_matches,
+                         float* out_scores, int* out_k, int* out_stop, cudaStream_t st) {
+  LightGlueState* s = ctx->lg;
+  if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "lightglue weights not set");
+  *out_k = 0;
+  *out_stop = 1;
+  if (n0 <= 0 || n1 <= 0) return B2_OK;  // lightglue.py:568-588 (no keypoints -> empty matches)
+  int rc;
+  const float* kps[2] = {kp0, kp1};
+  const float* descs[2] = {desc0, desc1};
+  const int ns[2] = {n0, n1};
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    if ((rc = lg_side_alloc(ctx, sd, ns[i]))) return rc;
+    B2_CUDA(ctx, cudaMemcpyAsync(sd.x[0].p, descs[i], (size_t)ns[i] * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    B2_LAUNCH(ctx, k_lg_posenc, 1, 1024, 0, st, kps[i], ns[i], s->wr, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>());
+    B2_CHECK_LAUNCH(ctx);
+  }
+  const bool do_stop = prm->depth_confidence > 0.0, do_prune = prm->width_confidence > 0.0;
+  const float keep_thr = (float)(1.0 - prm->width_confidence);  // scores > float32(1 - width_confidence)
+  int* counters = s->counters.as<int>();
+  int* hread = s->hread.as<int>();
+  int layer = 0;
+  for (layer = 0; layer < LG_LAYERS; ++layer) {
+    LgSide &a = s->side[0], &b = s->side[1];
+    if (a.n == 0 || b.n == 0) break;
+    if ((rc = lg_self_block(ctx, st, s, layer, a))) return rc;
+    if ((rc = lg_self_block(ctx, st, s, layer, b))) return rc;
+    if ((rc = lg_cross_block(ctx, st, s, layer))) return rc;
+    if (layer == LG_LAYERS - 1) break;
+    if (!do_stop && !do_prune) continue;
+    bool prune_side[2];
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
+      prune_side[i] = do_prune && sd.n > prm->prune_min_kpts;
+      const float* x = sd.x[sd.cur].as<float>();
+      B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, do_stop ? s->tw[layer].w : nullptr,
+                do_stop ? s->tw[layer].b : nullptr, prune_side[i] ? s->aw[layer].wm : nullptr,
+                prune_side[i] ? s->aw[layer].bm : nullptr, sd.conf.as<float>(), sd.mat.as<float>(), (float*)nullptr);
+      B2_CHECK_LAUNCH(ctx);
+      if (!do_stop) B2_CUDA(ctx, cudaMemsetAsync(sd.conf.p, 0, (size_t)sd.n * 4, st));  // confidences None -> never "<= thr"
+      if (!prune_side[i]) B2_CUDA(ctx, cudaMemsetAsync(sd.mat.p, 0x7f, (size_t)sd.n * 4, st));  // huge positive: keep all
+      B2_LAUNCH(ctx, k_lg_prune_plan, 1, 1024, 0, st, sd.conf.as<float>(), sd.mat.as<float>(), sd.n,
+                do_stop ? s->thr[layer] : -1.0f, keep_thr, i, sd.src.as<int>(), counters);
+      B2_CHECK_LAUNCH(ctx);
+      if (prune_side[i]) {
+        int nxt = sd.cur ^ 1;
+        B2_LAUNCH(ctx, k_lg_gather, cdiv(sd.n, 8), 256, 0, st, sd.src.as<int>(), counters + 2 + i, x,
+                  sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(),
+                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>());
+        B2_CHECK_LAUNCH(ctx);
+      }
+    }
+    B2_CUDA(ctx, cudaMemcpyAsync(hread, counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaStreamSynchronize(st));
+    if (do_stop) {
+      // check_if_stop (lightglue.py:645-656) in float32: 1 - (#unconfident / (m + n)) > depth_confidence
+      float ratio = 1.0f - (float)(hread[0] + hread[1]) / (float)(n0 + n1);
+      if (ratio > (float)prm->depth_confidence) break;
+    }
+    for (int i = 0; i < 2; ++i)
+      if (prune_side[i]) {
+        s->side[i].cur ^= 1;
+        s->side[i].n = hread[2 + i];
+      }
+  }
+  if (layer == LG_LAYERS) layer = LG_LAYERS - 1;
+  *out_stop = layer + 1;
+  LgSide &a = s->side[0], &b = s->side[1];
+  if (a.n == 0 || b.n == 0) return B2_OK;
+  // MatchAssignment (lightglue.py:280-296) at the stopping layer
+  const AssignW& aw = s->aw[layer];
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    const float* x = sd.x[sd.cur].as<float>();
+    GemmArgs g = gemm_linear(x, 256, 256, aw.wf, aw.bf, sd.md.as<float>(), 256, sd.n, 256);
+    g.scale = 0.25f;  // / 256 ** 0.25
+    if ((rc = launch_gemm(ctx, st, g))) return rc;
+    B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, (const float*)nullptr, (const float*)nullptr, aw.wm,
+              aw.bm, (float*)nullptr, (float*)nullptr, sd.ls.as<float>());
+    B2_CHECK_LAUNCH(ctx);
+  }
+  B2_CUDA(ctx, s->sim.ensure((size_t)a.n * b.n * 4));
+  GemmArgs gs = gemm_linear(a.md.as<float>(), 256, 256, b.md.as<float>(), nullptr, s->sim.as<float>(), b.n, a.n, b.n);
+  if ((rc = launch_gemm(ctx, st, gs))) return rc;
+  const float* sim = s->sim.as<float>();
+  B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 128), 128, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_lg_row_argmax, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+            b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 128), 128, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+            b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), b.aidx.as<int>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,
+            (float)prm->filter_threshold, a.ind[a.cur].as<int>(), b.ind[b.cur].as<int>(), out_matches, out_scores, counters + 4);
+  B2_CHECK_LAUNCH(ctx);
+  B2_CUDA(ctx, cudaMemcpyAsync(hread + 4, counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  *out_k = hread[4];
+  ctx->debug["lg_desc0"] = {a.x[a.cur].as<float>(), (int64_t)a.n * 256};
+  ctx->debug["lg_desc1"] = {b.x[b.cur].as<float>(), (int64_t)b.n * 256};
+  return B2_OK;
+}
+
+extern "C" int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
+                                      const float* desc1, int n1, const b2_lightglue_params* params, int64_t* out_matches,
+                                      float* out_scores, int* out_k, int* out_stop_layer, void* stream) {
+  if (!ctx || !params || !out_k || !out_stop_layer || n0 < 0 || n1 < 0) return B2_ERR_ARG;
+  if (n0 > 0 && n1 > 0 && (!kp0 || !desc0 || !kp1 || !desc1 || !out_matches)) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return lg_match_impl(ctx, kp0, desc0, n0, kp1, desc1, n1, params, (long long*)out_matches, out_scores, out_k,
+                       out_stop_layer, (cudaStream_t)stream);
+}
+
+extern "C" int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
+                                       const float* desc1, int n1, const b2_lightglue_params* params,
+                                       int64_t* out_matches, float* out_scores, int* out_k, int* out_stop_layer) {
+  if (!ctx || !params || !out_k || !out_stop_layer || n0 < 0 || n1 < 0) return B2_ERR_ARG;
+  *out_k = 0;
+  *out_stop_layer = 1;
+  if (n0 == 0 || n1 == 0) return B2_OK;
+  if (!kp0 || !desc0 || !kp1 || !desc1 || !out_matches) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int mk = n0 < n1 ? n0 : n1;
+  B2_CUDA(ctx, ctx->stage_d[0].ensure((size_t)n0 * 2 * 4));
+  B2_CUDA(ctx, ctx->stage_d[1].ensure((size_t)n0 * 256 * 4));
+  B2_CUDA(ctx, ctx->stage_d[2].ensure((size_t)n1 * 2 * 4));
+  B2_CUDA(ctx, ctx->stage_d[3].ensure((size_t)n1 * 256 * 4));
+  B2_CUDA(ctx, ctx->stage_d[5].ensure((size_t)mk * 2 * 8));
+  B2_CUDA(ctx, ctx->stage_d[6].ensure((size_t)mk * 4));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[0].p, kp0, (size_t)n0 * 2 * 4, cudaMemcpyHostToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[1].p, desc0, (size_t)n0 * 256 * 4, cudaMemcpyHostToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[2].p, kp1, (size_t)n1 * 2 * 4, cudaMemcpyHostToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[3].p, desc1, (size_t)n1 * 256 * 4, cudaMemcpyHostToDevice, st));
+  int rc = lg_match_impl(ctx, ctx->stage_d[0].as<float>(), ctx->stage_d[1].as<float>(), n0, ctx->stage_d[2].as<float>(),
+                         ctx->stage_d[3].as<float>(), n1, params, ctx->stage_d[5].as<long long>(),
+                         ctx->stage_d[6].as<float>(), out_k, out_stop_layer, st);
+  if (rc) return rc;
+  if (*out_k > 0) {
+    B2_CUDA(ctx, cudaMemcpyAsync(out_matches, ctx->stage_d[5].p, (size_t)*out_k * 2 * 8, cudaMemcpyDeviceToHost, st));
+    if (out_scores) B2_CUDA(ctx, cudaMemcpyAsync(out_scores, ctx->stage_d[6].p, (size_t)*out_k * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return B2_OK;
+}

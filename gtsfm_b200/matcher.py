@@ -1,0 +1,94 @@
+"""B200 LightGlue / SuperGlue matcher plugins.
+
+Drop-ins for gtsfm/frontend/matcher/lightglue_matcher.py:24-112 (`LightGlueMatcher`) and
+gtsfm/frontend/matcher/superglue_matcher.py:30-115 (`SuperGlueMatcher`): same `match(...)` signature, argument
+meaning, errors and output dtypes ((K, 2) int64 for LightGlue, uint32 for SuperGlue, rows ascending in column 0).
+All arithmetic runs in libgtsfm_b200.so; lazily created device state keeps the objects picklable
+(tests/frontend/matcher/test_matcher_base.py:102-107).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from . import _lib, weights
+from .gtsfm_api import Keypoints, MatcherBase
+
+DESC_DIM = 256
+
+
+class LightGlueEngine:
+    def __init__(self, state_dict, device: int = 0, ctx: Optional[_lib.Context] = None):
+        self.ctx = ctx or _lib.Context(device)
+        blob = weights.pack_lightglue(weights.load_state_dict(state_dict))
+        self.ctx.check(self.ctx.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
+
+    def match(self, kp0, desc0, kp1, desc1, depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1,
+              prune_min_kpts=-1, return_scores=False):
+        kp0 = np.ascontiguousarray(kp0, np.float32)
+        kp1 = np.ascontiguousarray(kp1, np.float32)
+        desc0 = np.ascontiguousarray(desc0, np.float32)
+        desc1 = np.ascontiguousarray(desc1, np.float32)
+        n0, n1 = len(kp0), len(kp1)
+        cap = max(1, min(n0, n1))
+        out = np.empty((cap, 2), np.int64)
+        sc = np.empty(cap, np.float32)
+        k, stop = _lib.C.c_int(0), _lib.C.c_int(0)
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, prune_min_kpts)
+        rc = self.ctx.lib.b2_lightglue_match_host(self.ctx.handle, _lib.ptr(kp0), _lib.ptr(desc0), n0, _lib.ptr(kp1),
+                                                  _lib.ptr(desc1), n1, _lib.C.byref(prm), _lib.ptr(out), _lib.ptr(sc),
+                                                  _lib.C.byref(k), _lib.C.byref(stop))
+        self.ctx.check(rc, "lightglue_match")
+        self.last_stop = stop.value
+        if return_scores:
+            return out[: k.value].copy(), sc[: k.value].copy()
+        return out[: k.value].copy()
+
+
+class B200LightGlueMatcher(MatcherBase):
+    """LightGlue on hand-written sm_100a kernels behind GTSfM's MatcherBase.
+
+    `cpu_semantics=True` (default) reproduces what the reference computes on its CPU front-end (pruning attempted at
+    every layer, lightglue.py:339-344) and is what the parity fixtures pin; False uses the reference's CUDA+flash
+    pruning threshold of 1536 keypoints.
+    """
+
+    def __init__(self, features: str = "superpoint", use_cuda: bool = True, weights_path: Union[Path, str, dict, None] = None,
+                 device: int = 0, cpu_semantics: bool = True):
+        super().__init__()
+        if features != "superpoint":
+            raise ValueError(f"Unsupported features: {features} (this build serves the SuperPoint LightGlue only)")
+        if weights_path is None:
+            raise FileNotFoundError("LightGlue weights_path is required (superpoint_lightglue_v0-1_arxiv.pth-style checkpoint)")
+        if not isinstance(weights_path, dict) and not Path(weights_path).exists():
+            raise FileNotFoundError(f"LightGlue weights not found at {weights_path}")
+        self._use_cuda = use_cuda
+        self._features = features
+        self._weights = weights_path
+        self._device = device
+        self._cpu_semantics = cpu_semantics
+        self._engine: Optional[LightGlueEngine] = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        return st
+
+    def _ensure_engine(self) -> LightGlueEngine:
+        if self._engine is None:
+            self._engine = LightGlueEngine(self._weights, self._device)
+        return self._engine
+
+    def match(self, keypoints_i1: Keypoints, keypoints_i2: Keypoints, descriptors_i1: np.ndarray, descriptors_i2: np.ndarray,
+              im_shape_i1: Tuple[int, int, int], im_shape_i2: Tuple[int, int, int]) -> np.ndarray:
+        if keypoints_i1.responses is None or keypoints_i2.responses is None:
+            raise ValueError("Responses for keypoints required for LightGlue.")  # lightglue_matcher.py:78-79
+        if len(keypoints_i1) == 0 or len(keypoints_i2) == 0:
+            return np.zeros((0, 2), np.int64)
+        if descriptors_i1.shape[1] != DESC_DIM or descriptors_i2.shape[1] != DESC_DIM:
+            raise AssertionError("LightGlue(superpoint) expects 256-dimensional descriptors")  # lightglue.py:509-510
+        eng = self._ensure_engine()
+        return eng.match(keypoints_i1.coordinates, descriptors_i1, keypoints_i2.coordinates, descriptors_i2,
+                         prune_min_kpts=-1 if self._cpu_semantics else 1536)

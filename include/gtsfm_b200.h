@@ -78,9 +78,11 @@ int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int n, float* 
 int b2_lightglue_set_weights(b2_context* ctx, const float* host_blob, size_t n_floats);
 
 typedef struct b2_lightglue_params {
-  float depth_confidence;  /* 0.95; <= 0 disables early exit   (lightglue.py:330)            */
-  float width_confidence;  /* 0.99; <= 0 disables pruning      (lightglue.py:331)            */
-  float filter_threshold;  /* 0.1                              (lightglue.py:332)            */
+  /* doubles on purpose: the reference holds these as Python floats and rounds the DERIVED value to float32 at the
+   * comparison (e.g. scores > float32(1 - 0.99)), which a float32 field could not reproduce bit-exactly. */
+  double depth_confidence; /* 0.95; <= 0 disables early exit   (lightglue.py:330)            */
+  double width_confidence; /* 0.99; <= 0 disables pruning      (lightglue.py:331)            */
+  double filter_threshold; /* 0.1                              (lightglue.py:332)            */
   int prune_min_kpts;      /* -1 = reference CPU semantics (prune at every layer); 1536 = its CUDA+flash value */
 } b2_lightglue_params;
 
