@@ -1,7 +1,6 @@
 // Entry points whose kernels are not built yet return B2_ERR_STATE with a message (never a silent fallback).
 #include "common.cuh"
 void sg_destroy(b2_context*) {}
-void rs_destroy(b2_context*) {}
 #define NOT_BUILT(ctx) b2_fail(ctx, B2_ERR_STATE, std::string(__func__) + ": not built yet")
 extern "C" {
 int b2_topk_indices_dev(b2_context* c, const float*, int, int, int32_t*, int*, void*) { return NOT_BUILT(c); }
@@ -10,9 +9,4 @@ int b2_superglue_match_dev(b2_context* c, const float*, const float*, const floa
                            const float*, const float*, int, int, int, int, float, uint32_t*, float*, int*, void*) { return NOT_BUILT(c); }
 int b2_superglue_match_host(b2_context* c, const float*, const float*, const float*, int, int, int, const float*,
                             const float*, const float*, int, int, int, int, float, uint32_t*, float*, int*) { return NOT_BUILT(c); }
-int b2_ransac_essential_host(b2_context* c, const double*, const double*, int, const b2_ransac_params*, double*,
-                             uint8_t*, int*, double*, double*) { return NOT_BUILT(c); }
-int b2_ransac_fundamental_host(b2_context* c, const double*, const double*, int, const b2_ransac_params*, double*,
-                               uint8_t*, int*) { return NOT_BUILT(c); }
-int b2_recover_pose_host(b2_context* c, const double*, const double*, const double*, int, double*, double*, int*) { return NOT_BUILT(c); }
 }

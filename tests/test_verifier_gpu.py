@@ -1,0 +1,95 @@
+"""GPU parity for the RANSAC verifier.  USAC cannot be matched bit-for-bit (SURVEY.md §7 hard part 4); the bar is the
+reference tests' own criteria (tests/frontend/verifier/test_verifier_base.py, test_ransac.py) plus agreement with the
+cv2 results stored in tests/golden/verifier_*.npz."""
+import pickle
+
+import numpy as np
+import pytest
+
+from gtsfm_b200.gtsfm_api import Cal3Bundler, Keypoints
+from gtsfm_b200.verifier import B200Ransac, RansacEngine
+from oracle import verifier_ref as vr
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL_DEG = 2.0  # ROTATION_ANGULAR_ERROR_DEG_THRESHOLD, test_verifier_base.py:24
+DIR_TOL_DEG = 2.0
+
+
+@pytest.mark.parametrize("use_intrinsics", [True, False])
+def test_two_plane_scene(use_intrinsics):
+    """test_verifier_base.py:81-100 for E (5pt) and F (8pt), thresholds as in test_ransac.py:11-30 (0.5 px)."""
+    uv1, uv2, R, t = vr.two_planes_scene(4, 4)
+    matches = np.stack([np.arange(8), np.arange(8)], -1).astype(np.uint32)
+    ver = B200Ransac(use_intrinsics_in_verification=use_intrinsics, estimation_threshold_px=0.5)
+    Rc, tc, rows, ratio = ver.verify(Keypoints(uv1), Keypoints(uv2), matches, Cal3Bundler(), Cal3Bundler())
+    assert vr.rot_angle_deg(R, Rc.matrix()) < ROT_TOL_DEG
+    assert vr.dir_angle_deg(t, tc.point3()) < DIR_TOL_DEG
+    assert np.array_equal(rows, matches) and rows.dtype == matches.dtype
+    assert ratio == 1.0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_agrees_with_cv2_on_seeded_scenes(golden_dir, seed):
+    fx = np.load(golden_dir / f"verifier_{seed}.npz")
+    kp1, kp2, matches, K, R, t, is_in = vr.synthetic_two_view(seed, int(fx["k"]), float(fx["ratio"]))
+    cal = Cal3Bundler(K[0], 0, 0, K[1], K[2])
+    ver = B200Ransac(True, 4.0)
+    Rc, tc, rows, ratio = ver.verify(Keypoints(kp1), Keypoints(kp2), matches, cal, cal)
+    assert vr.rot_angle_deg(R, Rc.matrix()) < 0.5 and vr.dir_angle_deg(t, tc.point3()) < 2.0
+    mine = set(rows[:, 0].tolist())
+    cv = set(fx["rows_cv"][:, 0].tolist())
+    gt = set(np.flatnonzero(is_in).tolist())
+    iou = len(mine & cv) / len(mine | cv)
+    assert iou > 0.97, f"inlier IoU vs cv2 {iou:.3f}"
+    assert len(gt - mine) <= 0.02 * len(gt), "missed true inliers"
+    assert abs(ratio - float(fx["ratio_cv"])) < 0.02
+    # F path (8-point)
+    verF = B200Ransac(False, 4.0)
+    Rf, tf, rowsf, ratiof = verF.verify(Keypoints(kp1), Keypoints(kp2), matches, cal, cal)
+    assert vr.rot_angle_deg(R, Rf.matrix()) < 1.5
+    mf, cvf = set(rowsf[:, 0].tolist()), set(fx["rows_cvF"][:, 0].tolist())
+    assert len(mf & cvf) / len(mf | cvf) > 0.95
+
+
+def test_inlier_definition_and_recover_pose(b200_ctx, golden_dir):
+    """mask == (squared Sampson < thr^2) under the returned E; recoverPose matches cv2's R, t for cv2's own E."""
+    fx = np.load(golden_dir / "verifier_2.npz")
+    kp1, kp2, matches, K, R, t, is_in = vr.synthetic_two_view(2, 1000, 0.8)
+    n1, n2 = vr.calibrate(kp1, *K), vr.calibrate(kp2, *K)
+    eng = RansacEngine(ctx=b200_ctx)
+    thr = 4.0 / K[0]
+    E, mask, Rg, tg = eng.essential(n1, n2, thr)
+    s = vr.sampson_sq(E, n1, n2)
+    assert np.array_equal(mask.astype(bool), s < thr * thr)
+    rows = fx["rows_cv"]
+    R2, t2, good = eng.recover_pose(fx["E_cv"], n1[rows[:, 0]], n2[rows[:, 1]])
+    assert vr.rot_angle_deg(fx["R_cv"], R2) < 1e-3 and vr.dir_angle_deg(fx["t_cv"], t2) < 1e-3
+    assert good == len(rows)
+
+
+def test_contract_degenerate_and_repro():
+    """Failure tuple, index validity on random input, picklability, run-to-run identity
+    (test_verifier_base.py:102-146, repro test SURVEY.md Appendix B)."""
+    ver = B200Ransac(True, 0.5)
+    pickle.dumps(ver)
+    assert repr(ver) == "B200Ransac__use_intrinsicsTrue_0.5px"
+    rng = np.random.default_rng(0)
+    kp1 = Keypoints(rng.uniform(0, 300, (50, 2)))
+    kp2 = Keypoints(rng.uniform(0, 300, (60, 2)))
+    cal = Cal3Bundler(200, 0, 0, 150, 150)
+    for m in (np.zeros((0, 2), np.uint32), np.array([[0, 0], [1, 1], [2, 2], [3, 3], [4, 4]], np.uint32)):
+        R, t, rows, ratio = ver.verify(kp1, kp2, m, cal, cal)
+        assert R is None and t is None and rows.size == 0 and ratio == 0.0
+    matches = np.stack([rng.permutation(50)[:40], rng.permutation(60)[:40]], -1).astype(np.uint32)
+    R, t, rows, ratio = ver.verify(kp1, kp2, matches, cal, cal)
+    pickle.dumps(ver)
+    if rows.size:
+        assert np.all(rows[:, 0] < 50) and np.all(rows[:, 1] < 60)
+    kpa, kpb, m2, K, *_ = vr.synthetic_two_view(9, 400, 0.5)
+    cal2 = Cal3Bundler(K[0], 0, 0, K[1], K[2])
+    v2 = B200Ransac(True, 4.0)
+    first = v2.verify(Keypoints(kpa), Keypoints(kpb), m2, cal2, cal2)
+    for _ in range(3):
+        again = v2.verify(Keypoints(kpa), Keypoints(kpb), m2, cal2, cal2)
+        assert np.array_equal(first[0].matrix(), again[0].matrix()) and np.array_equal(first[2], again[2])
