@@ -35,6 +35,8 @@ SIGNATURES = {
     "b2_destroy": (None, [_vp]),
     "b2_last_error": (C.c_char_p, [_vp]),
     "b2_launch_count": (C.c_uint64, [_vp]),
+    "b2_profile_start": (_i, [_vp, C.c_char_p]),
+    "b2_profile_stop": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "b2_debug_fetch": (C.c_int64, [_vp, C.c_char_p, _vp, C.c_int64]),
     "b2_superpoint_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_superpoint_detect_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _f, _i, _i, _vp, _vp, _i, _ip, _vp]),
@@ -50,6 +52,7 @@ SIGNATURES = {
     "b2_superglue_match_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _ip]),
     "b2_ransac_essential_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(RansacParams), _vp, _vp, _ip, _vp, _vp]),
     "b2_ransac_fundamental_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(RansacParams), _vp, _vp, _ip]),
+    "b2_ransac_essential_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, C.POINTER(RansacParams), _vp, _vp, _ip, _vp, _vp, _vp]),
     "b2_recover_pose_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _ip]),
 }
 
@@ -106,6 +109,14 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.b2_launch_count(self.handle))
+
+    def profile_start(self, kernel_prefix: str) -> None:
+        self.check(self._lib.b2_profile_start(self.handle, kernel_prefix.encode()), "profile_start")
+
+    def profile_stop(self):
+        ms, n, w = C.c_double(0), C.c_uint64(0), C.c_double(0)
+        self.check(self._lib.b2_profile_stop(self.handle, C.byref(ms), C.byref(n), C.byref(w)), "profile_stop")
+        return ms.value, int(n.value), w.value
 
     def debug_fetch(self, name: str, max_floats: int) -> np.ndarray:
         out = np.empty(max_floats, np.float32)

@@ -33,6 +33,7 @@ extern "C" void b2_destroy(b2_context* ctx) {
   rs_destroy(ctx);
   for (auto& b : ctx->stage_d) b.release();
   for (auto& b : ctx->stage_h) b.release();
+  for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -52,4 +53,33 @@ extern "C" int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host
   if (cudaMemcpy(host_out, it->second.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
     return b2_fail(ctx, B2_ERR_CUDA, "debug fetch copy failed");
   return n;
+}
+
+extern "C" int b2_profile_start(b2_context* ctx, const char* kernel_prefix) {
+  if (!ctx || !kernel_prefix) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->prof.on = true;
+  ctx->prof.name = kernel_prefix;
+  ctx->prof.used = 0;
+  ctx->prof.work = 0.0;
+  return B2_OK;
+}
+
+extern "C" int b2_profile_stop(b2_context* ctx, double* total_ms, uint64_t* launches, double* work) {
+  if (!ctx) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  B2_CUDA(ctx, cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof.used; i += 2) {
+    float t = 0.f;
+    B2_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof.ev[i], ctx->prof.ev[i + 1]));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = ctx->prof.used / 2;
+  if (work) *work = ctx->prof.work;
+  ctx->prof.on = false;
+  ctx->prof.used = 0;
+  return B2_OK;
 }

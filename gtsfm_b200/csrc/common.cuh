@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
@@ -65,6 +66,17 @@ struct DebugView {
   int64_t n;
 };
 
+// live per-kernel timing for bench.py's roofline line: CUDA events recorded on the launching stream around every
+// launch whose kernel name starts with `name`, plus the algorithmic work (FLOP or bytes) those launches did.
+struct ProfState {
+  bool on = false;
+  std::string name;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  double work = 0.0;
+  bool match(const char* kernel) const { return on && strncmp(kernel, name.c_str(), name.size()) == 0; }
+};
+
 struct SuperPointState;
 struct LightGlueState;
 struct SuperGlueState;
@@ -76,6 +88,7 @@ struct b2_context {
   std::string err;
   std::mutex mu;
   uint64_t launches = 0;
+  ProfState prof;
   cudaStream_t stream = nullptr;  // owned; used by *_host entry points
   std::map<std::string, DebugView> debug;
   SuperPointState* sp = nullptr;
@@ -102,9 +115,25 @@ inline int b2_fail(b2_context* ctx, int code, const std::string& msg) {
   } while (0)
 
 // launch bookkeeping: every kernel launch of the library goes through this macro
+inline void b2_prof_mark(b2_context* ctx, cudaStream_t st) {
+  ProfState& p = ctx->prof;
+  if (p.used == p.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p.ev.push_back(e);
+  }
+  cudaEventRecord(p.ev[p.used++], st);
+}
+inline void b2_prof_work(b2_context* ctx, const char* kernel, double work) {
+  if (ctx->prof.match(kernel)) ctx->prof.work += work;
+}
+
 #define B2_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)  \
   do {                                                          \
+    const bool _prof = (ctx)->prof.match(#kernel);              \
+    if (_prof) b2_prof_mark((ctx), (stream));                   \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+    if (_prof) b2_prof_mark((ctx), (stream));                   \
     (ctx)->launches++;                                          \
   } while (0)
 

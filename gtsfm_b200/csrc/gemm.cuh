@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) k_gemm_nt(GemmArgs g) {
 static inline int launch_gemm(b2_context* ctx, cudaStream_t st, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return B2_OK;
   dim3 grid(cdiv(g.N, GB_N), cdiv(g.M, GB_M));
+  b2_prof_work(ctx, "k_gemm_nt", 2.0 * g.M * g.N * (g.K1 + g.K2));
   B2_LAUNCH(ctx, k_gemm_nt, grid, 256, 0, st, g);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
@@ -226,6 +227,7 @@ static inline int launch_flash(b2_context* ctx, cudaStream_t st, const float* Q,
                                int Nq, int Nk, float scale) {
   if (Nq <= 0) return B2_OK;
   dim3 grid(cdiv(Nq, FA_T), 4);
+  b2_prof_work(ctx, "k_flash_attn", 4.0 * 2.0 * 2.0 * (double)Nq * Nk * 64);  // 4 heads x (QK^T + PV) x 2 FLOP/MAC
   B2_LAUNCH(ctx, k_flash_attn, grid, 256, FA_SMEM, st, Q, K, V, O, Nq, Nk, scale);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;

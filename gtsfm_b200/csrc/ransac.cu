@@ -354,14 +354,33 @@ __global__ void __launch_bounds__(256) k_rs_pose(const double* __restrict__ E, c
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 
+// gather matched keypoints and calibrate them with a distortion-free pinhole model (utils/features.py:41-51 for
+// Cal3Bundler with k1 = k2 = 0): x = (u - u0) / f, in double.  f = 1, u0 = v0 = 0 leaves pixels (F path).
+__global__ void __launch_bounds__(256) k_rs_gather(const float* __restrict__ kp1, const float* __restrict__ kp2,
+                                                    const long long* __restrict__ matches, int k, double f1, double u1,
+                                                    double v1, double f2, double u2, double v2, double* __restrict__ x1,
+                                                    double* __restrict__ x2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  long long a = matches[2 * i], b = matches[2 * i + 1];
+  x1[2 * i] = ((double)kp1[2 * a] - u1) / f1;
+  x1[2 * i + 1] = ((double)kp1[2 * a + 1] - v1) / f1;
+  x2[2 * i] = ((double)kp2[2 * b] - u2) / f2;
+  x2[2 * i + 1] = ((double)kp2[2 * b + 1] - v2) / f2;
+}
+
+// x1 / x2 come either from host arrays (hx != null: uploaded here) or are already in s->x1 / s->x2 (device path).
+// out_mask: host pointer when mask_is_device == 0, device pointer otherwise.
 static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, const b2_ransac_params* prm, int mode,
-                  double* out_model, uint8_t* out_mask, int* out_ninl, double* out_R, double* out_t) {
+                  double* out_model, uint8_t* out_mask, int* out_ninl, double* out_R, double* out_t,
+                  cudaStream_t st = nullptr, int mask_is_device = 0) {
   if (!ctx->rs) ctx->rs = new RansacState();
   RansacState* s = ctx->rs;
-  cudaStream_t st = ctx->stream;
+  if (!st) st = ctx->stream;
   const int m = mode == 0 ? 5 : 8;
   *out_ninl = 0;
-  if (out_mask) memset(out_mask, 0, (size_t)k);
+  if (out_mask && !mask_is_device) memset(out_mask, 0, (size_t)k);
+  if (out_mask && mask_is_device && k > 0) B2_CUDA(ctx, cudaMemsetAsync(out_mask, 0, (size_t)k, st));
   if (k < m) return 1;
   const int hard_cap = mode == 0 ? 65536 : 262144;
   const int max_iters = prm->max_iters < 1 ? 1 : (prm->max_iters > hard_cap ? hard_cap : prm->max_iters);
@@ -377,8 +396,10 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
   B2_CUDA(ctx, s->mask.ensure((size_t)k + 16));
   B2_CUDA(ctx, s->pose.ensure(16 * 8));
   B2_CUDA(ctx, s->hbuf.ensure(sizeof(RsBest) + 16 * 8 + 64));
-  B2_CUDA(ctx, cudaMemcpyAsync(s->x1.p, hx1, (size_t)k * 16, cudaMemcpyHostToDevice, st));
-  B2_CUDA(ctx, cudaMemcpyAsync(s->x2.p, hx2, (size_t)k * 16, cudaMemcpyHostToDevice, st));
+  if (hx1) {
+    B2_CUDA(ctx, cudaMemcpyAsync(s->x1.p, hx1, (size_t)k * 16, cudaMemcpyHostToDevice, st));
+    B2_CUDA(ctx, cudaMemcpyAsync(s->x2.p, hx2, (size_t)k * 16, cudaMemcpyHostToDevice, st));
+  }
   B2_CUDA(ctx, cudaMemsetAsync(s->best.p, 0, sizeof(RsBest) + 16, st));
   RsBest* dbest = s->best.as<RsBest>();
   int* dcount = reinterpret_cast<int*>(s->best.as<char>() + sizeof(RsBest));
@@ -423,10 +444,11 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
   char* hb = s->hbuf.as<char>();
   B2_CUDA(ctx, cudaMemcpyAsync(hb, dbest, sizeof(RsBest) + 16, cudaMemcpyDeviceToHost, st));
   if (want_pose) B2_CUDA(ctx, cudaMemcpyAsync(hb + sizeof(RsBest) + 16, s->pose.p, 13 * 8, cudaMemcpyDeviceToHost, st));
-  if (out_mask) B2_CUDA(ctx, cudaMemcpyAsync(out_mask, s->mask.p, (size_t)k, cudaMemcpyDeviceToHost, st));
+  if (out_mask)
+    B2_CUDA(ctx, cudaMemcpyAsync(out_mask, s->mask.p, (size_t)k, mask_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
   if (!hbest->valid) {
-    if (out_mask) memset(out_mask, 0, (size_t)k);
+    if (out_mask && !mask_is_device) memset(out_mask, 0, (size_t)k);
     return 1;
   }
   memcpy(out_model, hbest->model, 9 * 8);
@@ -455,6 +477,29 @@ extern "C" int b2_ransac_fundamental_host(b2_context* ctx, const double* x1, con
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   return rs_run(ctx, x1, x2, k, params, 1, out_model, out_mask, out_num_inliers, nullptr, nullptr);
+}
+
+extern "C" int b2_ransac_essential_dev(b2_context* ctx, const float* kp1, const float* kp2, const int64_t* matches, int k,
+                                       const double* cal1, const double* cal2, const b2_ransac_params* params,
+                                       double* out_model, uint8_t* out_mask_dev, int* out_num_inliers, double* out_R,
+                                       double* out_t, void* stream) {
+  if (!ctx || !params || !out_model || !out_num_inliers || !cal1 || !cal2 || k < 0) return B2_ERR_ARG;
+  if (k > 0 && (!kp1 || !kp2 || !matches)) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (!ctx->rs) ctx->rs = new RansacState();
+  RansacState* s = ctx->rs;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k > 0) {
+    B2_CUDA(ctx, s->x1.ensure((size_t)k * 16));
+    B2_CUDA(ctx, s->x2.ensure((size_t)k * 16));
+    B2_LAUNCH(ctx, k_rs_gather, cdiv(k, 256), 256, 0, st, kp1, kp2, (const long long*)matches, k, cal1[0], cal1[1], cal1[2],
+              cal2[0], cal2[1], cal2[2], s->x1.as<double>(), s->x2.as<double>());
+    B2_CHECK_LAUNCH(ctx);
+  }
+  // rs_run uses the legacy stream when `stream` is NULL; the context stream otherwise stays unused here
+  return rs_run(ctx, nullptr, nullptr, k, params, 0, out_model, out_mask_dev, out_num_inliers, out_R, out_t,
+                st ? st : cudaStreamLegacy, 1);
 }
 
 extern "C" int b2_recover_pose_host(b2_context* ctx, const double* E, const double* x1, const double* x2, int k,

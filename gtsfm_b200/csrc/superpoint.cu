@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(256) k_sample_desc(const float* __restrict__ d
 static int sp_conv3x3(b2_context* ctx, cudaStream_t st, const float* in, int li, float* out, int H, int W, bool pool) {
   SuperPointState* s = ctx->sp;
   dim3 grid(cdiv(W, CT_W), cdiv(H, CT_H), SP_CO[li] / 64);
+  b2_prof_work(ctx, "k_conv3x3", 2.0 * 9.0 * H * W * SP_CI[li] * SP_CO[li]);
   if (pool)
     B2_LAUNCH(ctx, k_conv3x3<1>, grid, 256, 0, st, in, s->w[li], s->b[li], out, H, W, SP_CI[li], SP_CO[li]);
   else
@@ -695,6 +696,111 @@ extern "C" int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int
   int rc = sp_describe_impl(ctx, ctx->stage_d[3].as<float>(), n, ctx->stage_d[4].as<float>(), st);
   if (rc) return rc;
   B2_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->stage_d[4].p, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device top-k for the batched path: the k largest scores (ties at the k-th value -> lowest indices), kept in their
+// original (row-major) order.  4-pass 8-bit radix select on the float bit patterns (scores are positive), then an
+// ordered compaction.  Single CTA: n is a few 10^4.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_topk_select(const float* __restrict__ score, int n, int k, int* __restrict__ out_idx,
+                                                       int* __restrict__ out_count) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned prefix, need;
+  __shared__ int wtot[32];
+  __shared__ int carry, eq_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (k >= n) {
+    for (int i = threadIdx.x; i < n; i += 1024) out_idx[i] = i;
+    if (threadIdx.x == 0) *out_count = n;
+    return;
+  }
+  if (threadIdx.x == 0) prefix = 0, need = (unsigned)k;
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < 256; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) {
+      unsigned key = __float_as_uint(score[i]);
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned acc = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= need) break;
+        acc += hist[b];
+      }
+      need -= acc;  // how many still have to come from bin b
+      prefix |= ((unsigned)b) << shift;
+    }
+    __syncthreads();
+  }
+  // prefix = bit pattern of the k-th largest score; take everything above it and the first `need` equal to it
+  const unsigned T = prefix;
+  if (threadIdx.x == 0) carry = 0, eq_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned key = i < n ? __float_as_uint(score[i]) : 0u;
+    bool gt = i < n && key > T, eq = i < n && key == T;
+    // rank among equals, in index order
+    unsigned em = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) wtot[warp] = __popc(em);
+    __syncthreads();
+    if (warp == 0) {
+      int w = wtot[lane], ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += u;
+      }
+      wtot[lane] = ws - w;
+    }
+    __syncthreads();
+    int eq_rank = eq_carry + wtot[warp] + __popc(em & ((1u << lane) - 1));
+    bool take = gt || (eq && (unsigned)eq_rank < need);
+    __syncthreads();
+    if (threadIdx.x == 1023) eq_carry = eq_rank + (eq ? 1 : 0);
+    unsigned tm = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) wtot[warp] = __popc(tm);
+    __syncthreads();
+    if (warp == 0) {
+      int w = wtot[lane], ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += u;
+      }
+      wtot[lane] = ws - w;
+    }
+    __syncthreads();
+    int pos = carry + wtot[warp] + __popc(tm & ((1u << lane) - 1));
+    if (take) out_idx[pos] = i;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + (take ? 1 : 0);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_count = carry;
+}
+
+extern "C" int b2_topk_indices_dev(b2_context* ctx, const float* scores, int n, int k, int32_t* out_idx, int* out_k,
+                                   void* stream) {
+  if (!ctx || !out_k || n < 0 || k < 0 || (n > 0 && (!scores || !out_idx))) return B2_ERR_ARG;
+  *out_k = 0;
+  if (n == 0 || k == 0) return B2_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  B2_CUDA(ctx, ctx->stage_d[7].ensure(16));
+  B2_LAUNCH(ctx, k_topk_select, 1, 1024, 0, st, scores, n, k, (int*)out_idx, ctx->stage_d[7].as<int>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_CUDA(ctx, cudaMemcpyAsync(out_k, ctx->stage_d[7].p, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
   return B2_OK;
 }

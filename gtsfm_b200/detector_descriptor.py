@@ -33,6 +33,8 @@ class SuperPointEngine:
         self.ctx = ctx or _lib.Context(device)
         blob = weights.pack_superpoint(weights.load_state_dict(state_dict))
         self.ctx.check(self.ctx.lib.b2_superpoint_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superpoint_set_weights")
+        self.h2d_bytes = 0  # bytes this engine copied host->device / device->host (bench.py's e2e accounting)
+        self.d2h_bytes = 0
 
     @staticmethod
     def capacity(h: int, w: int) -> int:
@@ -53,12 +55,16 @@ class SuperPointEngine:
                                                     REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n))
         self.ctx.check(rc, "superpoint_detect")
         k = min(n.value, cap)
+        self.h2d_bytes += img.nbytes
+        self.d2h_bytes += k * 12 + 4
         return xy[:k].copy(), sc[:k].copy()
 
     def describe(self, xy: np.ndarray) -> np.ndarray:
         xy = np.ascontiguousarray(xy, np.float32)
         out = np.empty((len(xy), DESC_DIM), np.float32)
         self.ctx.check(self.ctx.lib.b2_superpoint_describe_host(self.ctx.handle, _lib.ptr(xy), len(xy), _lib.ptr(out)), "superpoint_describe")
+        self.h2d_bytes += xy.nbytes
+        self.d2h_bytes += out.nbytes
         return out
 
 

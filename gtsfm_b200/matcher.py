@@ -24,6 +24,8 @@ class LightGlueEngine:
         self.ctx = ctx or _lib.Context(device)
         blob = weights.pack_lightglue(weights.load_state_dict(state_dict))
         self.ctx.check(self.ctx.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     def match(self, kp0, desc0, kp1, desc1, depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1,
               prune_min_kpts=-1, return_scores=False):
@@ -42,6 +44,8 @@ class LightGlueEngine:
                                                   _lib.C.byref(k), _lib.C.byref(stop))
         self.ctx.check(rc, "lightglue_match")
         self.last_stop = stop.value
+        self.h2d_bytes += kp0.nbytes + kp1.nbytes + desc0.nbytes + desc1.nbytes
+        self.d2h_bytes += k.value * (16 + 4) + 8
         if return_scores:
             return out[: k.value].copy(), sc[: k.value].copy()
         return out[: k.value].copy()

@@ -1,0 +1,112 @@
+"""Device-resident batched front-end: detect -> top-k -> describe -> match -> verify with every tensor kept in HBM.
+
+This is the L2 seam of SURVEY.md §8b (`CorrespondenceGeneratorBase.generate_correspondences`): instead of one Dask task
+per image and per pair, each pickling ~5 MB of features (det_desc_correspondence_generator.py:65-85), one process per
+GPU walks its shard of the visibility graph and only small results (match index arrays, E / R / t) leave the device.
+PyTorch is used for device buffers and the stream only; all arithmetic is libgtsfm_b200.so through the `*_dev` C ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, weights
+from .detector_descriptor import KEYPOINT_THRESHOLD, NMS_RADIUS, REMOVE_BORDERS, SuperPointEngine
+from .verifier import DEFAULT_SEED, E_MAX_ITERS, RANSAC_SUCCESS_PROB
+
+
+@dataclass
+class DeviceFeatures:
+    kp: torch.Tensor  # (k, 2) float32 (x, y), device
+    score: torch.Tensor  # (k,)
+    desc: torch.Tensor  # (k, 256)
+    shape: Tuple[int, int]
+
+    def __len__(self) -> int:
+        return int(self.kp.shape[0])
+
+
+class DeviceFrontEnd:
+    def __init__(self, superpoint_sd, lightglue_sd=None, device: int = 0, max_keypoints: int = 5000, cpu_semantics: bool = True,
+                 ctx: Optional[_lib.Context] = None):
+        if not torch.cuda.is_available():
+            raise _lib.B200Error("DeviceFrontEnd needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        self.ctx = ctx or _lib.Context(device)
+        self.lib = self.ctx.lib
+        self.max_keypoints = max_keypoints
+        self.prune_min = -1 if cpu_semantics else 1536
+        blob = weights.pack_superpoint(weights.load_state_dict(superpoint_sd))
+        self.ctx.check(self.lib.b2_superpoint_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superpoint_set_weights")
+        if lightglue_sd is not None:
+            blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
+            self.ctx.check(self.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
+        self._scratch: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+    def _stream(self):
+        return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def detect(self, image: torch.Tensor) -> DeviceFeatures:
+        """image: uint8 device tensor (H, W) or (H, W, 3|4), contiguous."""
+        assert image.dtype == torch.uint8 and image.is_cuda and image.is_contiguous()
+        h, w = int(image.shape[0]), int(image.shape[1])
+        ch = 1 if image.dim() == 2 else int(image.shape[2])
+        cap = SuperPointEngine.capacity(h, w)
+        if cap not in self._scratch:
+            self._scratch[cap] = (torch.empty((cap, 2), dtype=torch.float32, device=self.device),
+                                  torch.empty(cap, dtype=torch.float32, device=self.device),
+                                  torch.empty(cap, dtype=torch.int32, device=self.device))
+        xy, sc, idx = self._scratch[cap]
+        n = _lib.C.c_int(0)
+        rc = self.lib.b2_superpoint_detect_dev(self.ctx.handle, _lib.ptr(image), h, w, ch, w * ch, KEYPOINT_THRESHOLD, NMS_RADIUS,
+                                               REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n), self._stream())
+        self.ctx.check(rc, "superpoint_detect_dev")
+        nk = min(n.value, cap)
+        k = _lib.C.c_int(0)
+        rc = self.lib.b2_topk_indices_dev(self.ctx.handle, _lib.ptr(sc), nk, self.max_keypoints, _lib.ptr(idx), _lib.C.byref(k), self._stream())
+        self.ctx.check(rc, "topk_indices_dev")
+        sel = idx[: k.value].long()
+        kp = xy[:nk].index_select(0, sel).contiguous()
+        score = sc[:nk].index_select(0, sel).contiguous()
+        desc = torch.empty((k.value, 256), dtype=torch.float32, device=self.device)
+        rc = self.lib.b2_superpoint_describe_dev(self.ctx.handle, _lib.ptr(kp), k.value, _lib.ptr(desc), self._stream())
+        self.ctx.check(rc, "superpoint_describe_dev")
+        return DeviceFeatures(kp, score, desc, (h, w))
+
+    def match(self, a: DeviceFeatures, b: DeviceFeatures, depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1):
+        cap = max(1, min(len(a), len(b)))
+        out = torch.empty((cap, 2), dtype=torch.int64, device=self.device)
+        k, stop = _lib.C.c_int(0), _lib.C.c_int(0)
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min)
+        rc = self.lib.b2_lightglue_match_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(a.desc), len(a), _lib.ptr(b.kp), _lib.ptr(b.desc),
+                                             len(b), _lib.C.byref(prm), _lib.ptr(out), None, _lib.C.byref(k), _lib.C.byref(stop),
+                                             self._stream())
+        self.ctx.check(rc, "lightglue_match_dev")
+        return out[: k.value], stop.value
+
+    def verify(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1: Sequence[float], cal2: Sequence[float],
+               threshold_px: float = 4.0, seed: int = DEFAULT_SEED):
+        """cal = (f, u0, v0).  -> (E (3,3) | None, R, t, num_inliers, mask device tensor)."""
+        k = int(matches.shape[0])
+        mask = torch.zeros(max(k, 1), dtype=torch.uint8, device=self.device)
+        if k < 6:  # opencv_verifier_base.py:70-79
+            return None, None, None, 0, mask[:k]
+        E, R, t = np.zeros(9), np.zeros(9), np.zeros(3)
+        c1, c2 = np.asarray(cal1, np.float64), np.asarray(cal2, np.float64)
+        n = _lib.C.c_int(0)
+        prm = _lib.RansacParams(threshold_px / max(c1[0], c2[0]), RANSAC_SUCCESS_PROB, E_MAX_ITERS, seed)
+        rc = self.lib.b2_ransac_essential_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(b.kp), _lib.ptr(matches.contiguous()), k, _lib.ptr(c1),
+                                              _lib.ptr(c2), _lib.C.byref(prm), _lib.ptr(E), _lib.ptr(mask), _lib.C.byref(n), _lib.ptr(R),
+                                              _lib.ptr(t), self._stream())
+        self.ctx.check(rc, "ransac_essential_dev")
+        if rc == 1:
+            return None, None, None, 0, mask[:k]
+        return E.reshape(3, 3), R.reshape(3, 3), t, n.value, mask[:k]
+
+
+def shard_pairs(pairs: List[Tuple[int, int]], rank: int, world: int) -> List[Tuple[int, int]]:
+    """Pair p (in visibility-graph order) -> GPU p mod world: no data-path collective."""
+    return [p for i, p in enumerate(pairs) if i % world == rank]

@@ -65,6 +65,7 @@ def lightglue_state_dict(seed: int = 2, profile: str = "full") -> Dict[str, np.n
     * ``"stop"``   – confidence bias rises with depth: early exit fires around layer 4-5.
     * ``"sharp"``  – as "stop" with a 160x identity ``final_proj``: separates the nearly collinear descriptors a
       random-weight SuperPoint produces on real images (mean pairwise cosine 0.97), for detect->match chain fixtures.
+    * ``"bench"``  – as "full" (all 9 layers, nothing pruned: the maximum-work path) with the sharp ``final_proj``.
     """
     rng = np.random.default_rng(seed)
     sd: Dict[str, np.ndarray] = {}
@@ -89,7 +90,7 @@ def lightglue_state_dict(seed: int = 2, profile: str = "full") -> Dict[str, np.n
     for i in range(9):
         p = f"log_assignment.{i}."
         w, b = _lin(rng, d, d, gain=0.15, bias_std=0.0)
-        fgain = 160.0 if profile == "sharp" else 18.0
+        fgain = 160.0 if profile in ("sharp", "bench") else 18.0
         sd[p + "final_proj.weight"] = (w + fgain * np.eye(d, dtype=np.float32)).astype(np.float32)
         sd[p + "final_proj.bias"] = b
         mw = rng.standard_normal((1, d)).astype(np.float32)
@@ -216,3 +217,12 @@ def synthetic_features(seed: int, n0: int, n1: int, height: int = 480, width: in
     gt[src] = inv[:n_shared]
     sc1 = rng.uniform(0.005, 0.3, n1).astype(np.float32)
     return kp0, sc0, d0, kp1, sc1, d1, gt
+
+
+def synthetic_sequence(n_frames: int, height: int = 480, width: int = 640, step_px: int = 8, seed: int = 77):
+    """Frames of a camera translating over one seeded texture: frame i is the crop at x = step_px * i (multiples of 8 keep
+    the SuperPoint cell grid aligned, so a random-weight network still yields repeatable descriptors across frames).
+    -> list of (H, W, 3) uint8 arrays, and the pinhole calibration (f, u0, v0) used by the verifier."""
+    big = synthetic_frame(seed, height + 16, width + step_px * n_frames + 16, n_shapes=600 + 40 * n_frames)
+    frames = [np.ascontiguousarray(big[8 * (i % 2): 8 * (i % 2) + height, step_px * i: step_px * i + width]) for i in range(n_frames)]
+    return frames, (0.9 * width, width / 2.0, height / 2.0)

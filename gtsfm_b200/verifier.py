@@ -37,6 +37,8 @@ def normalize_coordinates(coordinates: np.ndarray, intrinsics) -> np.ndarray:
 class RansacEngine:
     def __init__(self, device: int = 0, ctx: Optional[_lib.Context] = None):
         self.ctx = ctx or _lib.Context(device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     def essential(self, x1, x2, threshold, confidence=RANSAC_SUCCESS_PROB, max_iters=E_MAX_ITERS, seed=DEFAULT_SEED):
         x1 = np.ascontiguousarray(x1, np.float64)
@@ -49,6 +51,8 @@ class RansacEngine:
         rc = self.ctx.lib.b2_ransac_essential_host(self.ctx.handle, _lib.ptr(x1), _lib.ptr(x2), k, _lib.C.byref(prm), _lib.ptr(E),
                                                    _lib.ptr(mask), _lib.C.byref(n), _lib.ptr(R), _lib.ptr(t))
         self.ctx.check(rc, "ransac_essential")
+        self.h2d_bytes += x1.nbytes + x2.nbytes
+        self.d2h_bytes += k + 8 * 21 + 4
         if rc == 1:
             return None, mask[:k], None, None
         return E.reshape(3, 3), mask[:k], R.reshape(3, 3), t
@@ -64,6 +68,8 @@ class RansacEngine:
         rc = self.ctx.lib.b2_ransac_fundamental_host(self.ctx.handle, _lib.ptr(x1), _lib.ptr(x2), k, _lib.C.byref(prm), _lib.ptr(F),
                                                      _lib.ptr(mask), _lib.C.byref(n))
         self.ctx.check(rc, "ransac_fundamental")
+        self.h2d_bytes += x1.nbytes + x2.nbytes
+        self.d2h_bytes += k + 8 * 9 + 4
         if rc == 1:
             return None, mask[:k]
         return F.reshape(3, 3), mask[:k]

@@ -41,6 +41,11 @@ void b2_destroy(b2_context* ctx);
 const char* b2_last_error(const b2_context* ctx);
 /* Number of kernels this library has launched through `ctx` since creation (bench.py's "gpu_launches"). */
 uint64_t b2_launch_count(const b2_context* ctx);
+/* Live kernel timing for roofline reporting: CUDA events on the launching stream around every launch whose kernel name
+ * starts with `kernel_prefix` (e.g. "k_flash_attn"), until b2_profile_stop, which returns the summed device time, the
+ * number of such launches and the algorithmic work (FLOP) they performed. */
+int b2_profile_start(b2_context* ctx, const char* kernel_prefix);
+int b2_profile_stop(b2_context* ctx, double* total_ms, uint64_t* launches, double* work);
 /* Copies a named intermediate device buffer of the last call to host (tests only). Returns #floats written or <0. */
 int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host_out, int64_t max_floats);
 
@@ -129,6 +134,13 @@ int b2_ransac_essential_host(b2_context* ctx, const double* x1, const double* x2
 int b2_ransac_fundamental_host(b2_context* ctx, const double* x1, const double* x2, int k,
                                const b2_ransac_params* params, double* out_model, uint8_t* out_mask,
                                int* out_num_inliers);
+/* Device-resident variant for the batched path: kp1 / kp2 are DEVICE [n][2] float pixel coordinates, matches DEVICE
+ * [k][2] int64 rows; cal1 / cal2 are HOST {f, u0, v0} of distortion-free pinhole cameras (Cal3Bundler with k1 = k2 = 0,
+ * gtsfm/utils/features.py:41-51).  The threshold in `params` is in calibrated units (thr_px / max(f)).  out_mask_dev is a
+ * DEVICE [k] uint8 buffer (or NULL); the small outputs are HOST.  Synchronises `stream`. */
+int b2_ransac_essential_dev(b2_context* ctx, const float* kp1, const float* kp2, const int64_t* matches, int k,
+                            const double* cal1, const double* cal2, const b2_ransac_params* params, double* out_model,
+                            uint8_t* out_mask_dev, int* out_num_inliers, double* out_R, double* out_t, void* stream);
 /* cv2.recoverPose restated: decompose E, pick (R, t) with most points in front of both cameras. */
 int b2_recover_pose_host(b2_context* ctx, const double* E, const double* x1, const double* x2, int k, double* out_R,
                          double* out_t, int* out_num_good);
