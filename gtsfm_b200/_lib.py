@@ -38,6 +38,7 @@ SIGNATURES = {
     "b2_profile_start": (_i, [_vp, C.c_char_p]),
     "b2_profile_stop": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "b2_debug_fetch": (C.c_int64, [_vp, C.c_char_p, _vp, C.c_int64]),
+    "b2_debug_gemm_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "b2_superpoint_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_superpoint_detect_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _f, _i, _i, _vp, _vp, _i, _ip, _vp]),
     "b2_superpoint_describe_dev": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -1,0 +1,55 @@
+// Test-only entry points: run one GEMM through the SIMT fp32 kernel or the tcgen05 split-fp16 kernel (parity tests).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gemm_tc.cuh"
+
+extern "C" int b2_debug_gemm_host(b2_context* ctx, int mode, const float* A, const float* B, const float* bias, float* C,
+                                  int M, int N, int K) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0 || (K % 64)) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  DevBuf dA, dB, dC, dBias, dBh, dBl, dErr;
+  B2_CUDA(ctx, dA.ensure((size_t)M * K * 4));
+  B2_CUDA(ctx, dB.ensure((size_t)N * K * 4));
+  B2_CUDA(ctx, dC.ensure((size_t)M * N * 4));
+  B2_CUDA(ctx, dBias.ensure((size_t)N * 4));
+  B2_CUDA(ctx, dErr.ensure(16));
+  B2_CUDA(ctx, cudaMemcpyAsync(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(dB.p, B, (size_t)N * K * 4, cudaMemcpyHostToDevice, st));
+  if (bias) B2_CUDA(ctx, cudaMemcpyAsync(dBias.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  B2_CUDA(ctx, cudaMemsetAsync(dErr.p, 0, 16, st));
+  int rc = B2_OK;
+  if (mode == 0) {
+    rc = launch_gemm(ctx, st, gemm_linear(dA.as<float>(), K, K, dB.as<float>(), bias ? dBias.as<float>() : nullptr, dC.as<float>(), N, M, N));
+  } else {
+    GemmTcArgs g{};
+    g.A1 = dA.as<float>(), g.lda1 = K, g.K1 = K, g.ldb = K, g.C = dC.as<float>(), g.ldc = N, g.M = M, g.N = N;
+    g.bias = bias ? dBias.as<float>() : nullptr, g.scale = 1.f, g.err_flag = dErr.as<int>();
+    dim3 grid(cdiv(N, TC_N), cdiv(M, TC_M));
+    if (mode == 1) {
+      g.Bf = dB.as<float>();
+      B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+      B2_LAUNCH(ctx, k_gemm_tc<true>, grid, 128, TC_GEMM_SMEM, st, g);
+    } else {
+      B2_CUDA(ctx, dBh.ensure((size_t)N * K * 2));
+      B2_CUDA(ctx, dBl.ensure((size_t)N * K * 2));
+      B2_LAUNCH(ctx, k_split_f32, (unsigned)(((size_t)N * K + 255) / 256), 256, 0, st, dB.as<float>(), (size_t)N * K,
+                dBh.as<__half>(), dBl.as<__half>());
+      g.Bh = dBh.as<__half>(), g.Bl = dBl.as<__half>();
+      B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+      B2_LAUNCH(ctx, k_gemm_tc<false>, grid, 128, TC_GEMM_SMEM, st, g);
+    }
+    B2_CHECK_LAUNCH(ctx);
+  }
+  int err = 0;
+  if (rc == B2_OK) {
+    cudaError_t e = cudaMemcpyAsync(C, dC.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&err, dErr.p, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = b2_fail(ctx, B2_ERR_CUDA, std::string("debug gemm: ") + cudaGetErrorString(e));
+  }
+  dA.release(), dB.release(), dC.release(), dBias.release(), dBh.release(), dBl.release(), dErr.release();
+  if (rc == B2_OK && err) rc = b2_fail(ctx, B2_ERR_STATE, "tcgen05 pipeline timed out on an mbarrier (kernel bug)");
+  return rc;
+}

@@ -25,7 +25,7 @@ struct GemmArgs {
 
 constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
 
-__global__ void __launch_bounds__(256) k_gemm_nt(GemmArgs g) {
+static __global__ void __launch_bounds__(256) k_gemm_nt(GemmArgs g) {
   __shared__ __align__(16) float As[GB_K][GB_M + 4];
   __shared__ __align__(16) float Bs[GB_K][GB_N + 4];
   const int t = threadIdx.x;
@@ -109,7 +109,7 @@ static inline GemmArgs gemm_linear(const float* x, int ldx, int K, const float* 
 constexpr int FA_T = 64;
 constexpr size_t FA_SMEM = 4 * FA_T * 64 * sizeof(float);
 
-__global__ void __launch_bounds__(256) k_flash_attn(const float* __restrict__ Q, const float* __restrict__ Kp,
+static __global__ void __launch_bounds__(256) k_flash_attn(const float* __restrict__ Q, const float* __restrict__ Kp,
                                                      const float* __restrict__ V, float* __restrict__ O, int Nq, int Nk,
                                                      float scale) {
   extern __shared__ __align__(16) float fsm[];

@@ -8,8 +8,12 @@
 //
 // HBM layout: residual streams [N][256] fp32 row-major; attention operands head-major [4][N][64]; rotary table
 // cos/sin [N][32]; the (N0 x N1) similarity of the final assignment is materialised once in fp32.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 
 namespace {
 constexpr int LG_LAYERS = 9;
@@ -38,7 +42,8 @@ struct LgSide {  // per-image workspace
 
 struct LightGlueState {
   bool loaded = false;
-  DevBuf wblob;
+  DevBuf wblob, wblob_h, wblob_l, errflag;  // fp32 weights + their split-fp16 (hi, lo * 2^11) copies for tcgen05
+  bool use_tc = true;                          // B2_FORCE_SIMT=1 keeps every GEMM on the exact-fp32 SIMT kernel
   float* wr = nullptr;
   SelfW sw[LG_LAYERS];
   CrossW cw[LG_LAYERS];
@@ -54,6 +59,9 @@ void lg_destroy(b2_context* ctx) {
   if (!ctx->lg) return;
   LightGlueState* s = ctx->lg;
   s->wblob.release();
+  s->wblob_h.release();
+  s->wblob_l.release();
+  s->errflag.release();
   for (auto& sd : s->side) {
     DevBuf* bufs[] = {&sd.x[0], &sd.x[1], &sd.qkv, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.cs[0], &sd.cs[1],
                       &sd.sn[0], &sd.sn[1], &sd.ind[0], &sd.ind[1], &sd.conf, &sd.mat, &sd.src, &sd.md, &sd.rmax,
@@ -441,10 +449,58 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
     t = t < 0 ? 0 : (t > 1 ? 1 : t);
     s->thr[i] = (float)t;
   }
+  B2_CUDA(ctx, s->wblob_h.ensure(total * sizeof(__half)));
+  B2_CUDA(ctx, s->wblob_l.ensure(total * sizeof(__half)));
+  B2_CUDA(ctx, s->errflag.ensure(16));
+  B2_CUDA(ctx, cudaMemset(s->errflag.p, 0, 16));
+  B2_LAUNCH(ctx, k_split_f32, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)0, s->wblob.as<float>(), total,
+            s->wblob_h.as<__half>(), s->wblob_l.as<__half>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_CUDA(ctx, cudaDeviceSynchronize());
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+  {
+    const char* e = getenv("B2_FORCE_SIMT");
+    s->use_tc = !(e && e[0] == '1');
+  }
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   B2_CUDA(ctx, s->hread.ensure(64));
   B2_CUDA(ctx, s->counters.ensure(64));
   s->loaded = true;
+  return B2_OK;
+}
+
+// GEMM dispatch: tcgen05 split-fp16 kernel (weights pre-split, or an fp32 B operand converted in-kernel), or the
+// SIMT fp32 kernel when forced.  `b_is_weight` says g.B points into the weight blob.
+static int lg_gemm(b2_context* ctx, cudaStream_t st, LightGlueState* s, const GemmArgs& g, bool b_is_weight) {
+  if (!s->use_tc || ((g.K1 + g.K2) % TC_K) != 0 || (g.K1 % TC_K) != 0) return launch_gemm(ctx, st, g);
+  if (g.M <= 0 || g.N <= 0) return B2_OK;
+  GemmTcArgs t{};
+  t.A1 = g.A1, t.lda1 = g.lda1, t.K1 = g.K1, t.A2 = g.A2, t.lda2 = g.lda2, t.K2 = g.K2, t.ldb = g.ldb;
+  t.C = g.C, t.ldc = g.ldc, t.M = g.M, t.N = g.N, t.bias = g.bias, t.resid = g.resid, t.ldr = g.ldr, t.scale = g.scale;
+  t.head_major = g.head_major, t.err_flag = s->errflag.as<int>();
+  dim3 grid(cdiv(g.N, TC_N), cdiv(g.M, TC_M));
+  b2_prof_work(ctx, "k_gemm_tc", 2.0 * g.M * g.N * (g.K1 + g.K2));
+  if (b_is_weight) {
+    const size_t off = (size_t)(g.B - s->wblob.as<float>());
+    t.Bh = s->wblob_h.as<__half>() + off, t.Bl = s->wblob_l.as<__half>() + off;
+    B2_LAUNCH(ctx, k_gemm_tc<false>, grid, 128, TC_GEMM_SMEM, st, t);
+  } else {
+    t.Bf = g.B;
+    B2_LAUNCH(ctx, k_gemm_tc<true>, grid, 128, TC_GEMM_SMEM, st, t);
+  }
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+
+static int lg_flash(b2_context* ctx, cudaStream_t st, LightGlueState* s, const float* Q, const float* K, const float* V,
+                    float* O, int Nq, int Nk, float scale) {
+  if (!s->use_tc) return launch_flash(ctx, st, Q, K, V, O, Nq, Nk, scale);
+  if (Nq <= 0) return B2_OK;
+  b2_prof_work(ctx, "k_flash_tc", 4.0 * 2.0 * 2.0 * (double)Nq * Nk * 64);  // 4 heads x (QK^T + PV) x 2 FLOP/MAC
+  B2_LAUNCH(ctx, k_flash_tc, dim3(cdiv(Nq, AT_Q), 4), 128, AT_SMEM, st, Q, K, V, O, Nq, Nk, scale, s->errflag.as<int>());
+  B2_CHECK_LAUNCH(ctx);
   return B2_OK;
 }
 
@@ -472,19 +528,19 @@ static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
 }
 
 // x + ffn(cat[x, msg])  (lightglue.py:152-157,172,228-229): Linear(512,512) -> LN -> GELU -> Linear(512,256) + x
-static int lg_ffn(b2_context* ctx, cudaStream_t st, LgSide& sd, const float* w0, const float* b0, const float* lng,
+static int lg_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, LgSide& sd, const float* w0, const float* b0, const float* lng,
                   const float* lnb, const float* w3, const float* b3) {
   const int n = sd.n;
   float* x = sd.x[sd.cur].as<float>();
   GemmArgs g = gemm_linear(x, 256, 256, w0, b0, sd.h.as<float>(), 512, n, 512);
   g.A2 = sd.msg.as<float>(), g.lda2 = 256, g.K2 = 256, g.ldb = 512;
   int rc;
-  if ((rc = launch_gemm(ctx, st, g))) return rc;
+  if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
   B2_LAUNCH(ctx, k_lg_ln_gelu, cdiv(n, 8), 256, 0, st, sd.h.as<float>(), n, lng, lnb);
   B2_CHECK_LAUNCH(ctx);
   GemmArgs g2 = gemm_linear(sd.h.as<float>(), 512, 512, w3, b3, x, 256, n, 256);
   g2.resid = x, g2.ldr = 256;  // in place: every element is read (as residual) and written by the same thread
-  return launch_gemm(ctx, st, g2);
+  return lg_gemm(ctx, st, s, g2, true);
 }
 
 static int lg_self_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer, LgSide& sd) {
@@ -492,13 +548,13 @@ static int lg_self_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, in
   const int n = sd.n;
   float* x = sd.x[sd.cur].as<float>();
   int rc;
-  if ((rc = launch_gemm(ctx, st, gemm_linear(x, 256, 256, w.wqkv, w.bqkv, sd.qkv.as<float>(), 768, n, 768)))) return rc;
+  if ((rc = lg_gemm(ctx, st, s, gemm_linear(x, 256, 256, w.wqkv, w.bqkv, sd.qkv.as<float>(), 768, n, 768), true))) return rc;
   B2_LAUNCH(ctx, k_lg_split_rotary, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
             sd.sn[sd.cur].as<float>(), n, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>());
   B2_CHECK_LAUNCH(ctx);
-  if ((rc = launch_flash(ctx, st, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>(), sd.ctx.as<float>(), n, n, 0.125f))) return rc;
-  if ((rc = launch_gemm(ctx, st, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, n, 256)))) return rc;
-  return lg_ffn(ctx, st, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
+  if ((rc = lg_flash(ctx, st, s, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>(), sd.ctx.as<float>(), n, n, 0.125f))) return rc;
+  if ((rc = lg_gemm(ctx, st, s, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, n, 256), true))) return rc;
+  return lg_ffn(ctx, st, s, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
 static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
@@ -509,20 +565,20 @@ static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, i
     float* x = sd.x[sd.cur].as<float>();
     GemmArgs g = gemm_linear(x, 256, 256, w.wqk, w.bqk, sd.q.as<float>(), 0, sd.n, 256);
     g.head_major = 1;
-    if ((rc = launch_gemm(ctx, st, g))) return rc;
+    if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
     GemmArgs gv = gemm_linear(x, 256, 256, w.wv, w.bv, sd.v.as<float>(), 0, sd.n, 256);
     gv.head_major = 1;
-    if ((rc = launch_gemm(ctx, st, gv))) return rc;
+    if ((rc = lg_gemm(ctx, st, s, gv, true))) return rc;
   }
   // m0 = softmax(s * qk0 qk1^T) v1 ; m1 = softmax(s * qk1 qk0^T) v0 with s = 64^-0.5 (the reference scales each
   // operand by 64^-0.25, lightglue.py:216-221)
   LgSide &a = s->side[0], &b = s->side[1];
-  if ((rc = launch_flash(ctx, st, a.q.as<float>(), b.q.as<float>(), b.v.as<float>(), a.ctx.as<float>(), a.n, b.n, 0.125f))) return rc;
-  if ((rc = launch_flash(ctx, st, b.q.as<float>(), a.q.as<float>(), a.v.as<float>(), b.ctx.as<float>(), b.n, a.n, 0.125f))) return rc;
+  if ((rc = lg_flash(ctx, st, s, a.q.as<float>(), b.q.as<float>(), b.v.as<float>(), a.ctx.as<float>(), a.n, b.n, 0.125f))) return rc;
+  if ((rc = lg_flash(ctx, st, s, b.q.as<float>(), a.q.as<float>(), a.v.as<float>(), b.ctx.as<float>(), b.n, a.n, 0.125f))) return rc;
   for (int i = 0; i < 2; ++i) {
     LgSide& sd = s->side[i];
-    if ((rc = launch_gemm(ctx, st, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, sd.n, 256)))) return rc;
-    if ((rc = lg_ffn(ctx, st, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3))) return rc;
+    if ((rc = lg_gemm(ctx, st, s, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, sd.n, 256), true))) return rc;
+    if ((rc = lg_ffn(ctx, st, s, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3))) return rc;
   }
   return B2_OK;
 }
@@ -605,14 +661,14 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
     const float* x = sd.x[sd.cur].as<float>();
     GemmArgs g = gemm_linear(x, 256, 256, aw.wf, aw.bf, sd.md.as<float>(), 256, sd.n, 256);
     g.scale = 0.25f;  // / 256 ** 0.25
-    if ((rc = launch_gemm(ctx, st, g))) return rc;
+    if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
     B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, (const float*)nullptr, (const float*)nullptr, aw.wm,
               aw.bm, (float*)nullptr, (float*)nullptr, sd.ls.as<float>());
     B2_CHECK_LAUNCH(ctx);
   }
   B2_CUDA(ctx, s->sim.ensure((size_t)a.n * b.n * 4));
   GemmArgs gs = gemm_linear(a.md.as<float>(), 256, 256, b.md.as<float>(), nullptr, s->sim.as<float>(), b.n, a.n, b.n);
-  if ((rc = launch_gemm(ctx, st, gs))) return rc;
+  if ((rc = lg_gemm(ctx, st, s, gs, false))) return rc;
   const float* sim = s->sim.as<float>();
   B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>());
   B2_CHECK_LAUNCH(ctx);
@@ -630,6 +686,12 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
   B2_CUDA(ctx, cudaMemcpyAsync(hread + 4, counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
   *out_k = hread[4];
+  if (s->use_tc) {
+    int err = 0;
+    B2_CUDA(ctx, cudaMemcpyAsync(&err, s->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaStreamSynchronize(st));
+    if (err) return b2_fail(ctx, B2_ERR_STATE, "tcgen05 pipeline timed out on an mbarrier (kernel bug)");
+  }
   ctx->debug["lg_desc0"] = {a.x[a.cur].as<float>(), (int64_t)a.n * 256};
   ctx->debug["lg_desc1"] = {b.x[b.cur].as<float>(), (int64_t)b.n * 256};
   return B2_OK;

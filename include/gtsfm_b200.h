@@ -49,6 +49,11 @@ int b2_profile_stop(b2_context* ctx, double* total_ms, uint64_t* launches, doubl
 /* Copies a named intermediate device buffer of the last call to host (tests only). Returns #floats written or <0. */
 int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host_out, int64_t max_floats);
 
+/* Test-only: C[M,N] = A[M,K] * B[N,K]^T (+ bias) on HOST fp32 buffers.  mode 0 = SIMT fp32 kernel, 1 = tcgen05 split-fp16
+ * kernel with fp32 B converted in-kernel, 2 = tcgen05 split-fp16 kernel with pre-split fp16 B.  K must be a multiple of 64. */
+int b2_debug_gemm_host(b2_context* ctx, int mode, const float* A, const float* B, const float* bias, float* C, int M, int N,
+                       int K);
+
 /* ---- SuperPoint -------------------------------------------------------------------------------------------------- */
 /* `blob`: the 24 state-dict tensors in reference order (conv1a.weight, conv1a.bias, conv1b.weight, ... convDb.bias;
  * SURVEY.md Appendix A), OIHW fp32, concatenated.  n_floats must equal 1300865. */
