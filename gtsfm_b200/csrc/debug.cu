@@ -23,24 +23,23 @@ extern "C" int b2_debug_gemm_host(b2_context* ctx, int mode, const float* A, con
   if (mode == 0) {
     rc = launch_gemm(ctx, st, gemm_linear(dA.as<float>(), K, K, dB.as<float>(), bias ? dBias.as<float>() : nullptr, dC.as<float>(), N, M, N));
   } else {
+    // modes 1 and 2 both run the tcgen05 kernel on operands split here (A and B as fp16 hi / lo planes)
+    DevBuf dAh, dAl;
+    B2_CUDA(ctx, dAh.ensure((size_t)M * K * 2));
+    B2_CUDA(ctx, dAl.ensure((size_t)M * K * 2));
+    B2_CUDA(ctx, dBh.ensure((size_t)N * K * 2));
+    B2_CUDA(ctx, dBl.ensure((size_t)N * K * 2));
+    B2_LAUNCH(ctx, k_split_f32, (unsigned)(((size_t)M * K + 255) / 256), 256, 0, st, dA.as<float>(), (size_t)M * K, dAh.as<__half>(), dAl.as<__half>());
+    B2_LAUNCH(ctx, k_split_f32, (unsigned)(((size_t)N * K + 255) / 256), 256, 0, st, dB.as<float>(), (size_t)N * K, dBh.as<__half>(), dBl.as<__half>());
     GemmTcArgs g{};
-    g.A1 = dA.as<float>(), g.lda1 = K, g.K1 = K, g.ldb = K, g.C = dC.as<float>(), g.ldc = N, g.M = M, g.N = N;
-    g.bias = bias ? dBias.as<float>() : nullptr, g.scale = 1.f, g.err_flag = dErr.as<int>();
-    dim3 grid(cdiv(N, TC_N), cdiv(M, TC_M));
-    if (mode == 1) {
-      g.Bf = dB.as<float>();
-      B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
-      B2_LAUNCH(ctx, k_gemm_tc<true>, grid, 128, TC_GEMM_SMEM, st, g);
-    } else {
-      B2_CUDA(ctx, dBh.ensure((size_t)N * K * 2));
-      B2_CUDA(ctx, dBl.ensure((size_t)N * K * 2));
-      B2_LAUNCH(ctx, k_split_f32, (unsigned)(((size_t)N * K + 255) / 256), 256, 0, st, dB.as<float>(), (size_t)N * K,
-                dBh.as<__half>(), dBl.as<__half>());
-      g.Bh = dBh.as<__half>(), g.Bl = dBl.as<__half>();
-      B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
-      B2_LAUNCH(ctx, k_gemm_tc<false>, grid, 128, TC_GEMM_SMEM, st, g);
-    }
+    g.p[0].A1h = dAh.as<__half>(), g.p[0].A1l = dAl.as<__half>(), g.lda1 = K, g.K1 = K, g.Bh = dBh.as<__half>(), g.Bl = dBl.as<__half>(), g.ldb = K;
+    g.p[0].C = dC.as<float>(), g.ldc = N, g.p[0].M = M, g.N = N, g.bias = bias ? dBias.as<float>() : nullptr, g.scale = 1.f, g.err_flag = dErr.as<int>();
+    dim3 grid(cdiv(N, TC_N), cdiv(M, TC_M), 1);
+    B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+    B2_LAUNCH(ctx, k_gemm_tc, grid, 128, TC_GEMM_SMEM, st, g);
     B2_CHECK_LAUNCH(ctx);
+    B2_CUDA(ctx, cudaStreamSynchronize(st));
+    dAh.release(), dAl.release();
   }
   int err = 0;
   if (rc == B2_OK) {

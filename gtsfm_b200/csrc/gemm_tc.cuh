@@ -1,171 +1,195 @@
 // tcgen05 split-fp16 "NT" GEMM: C[M,N] = [A1 | A2][M,K] * B[N,K]^T with ~fp32 accuracy on the 5th-gen tensor cores.
 //
-// Each fp32 operand x is split as x ~= hi + lo * 2^-11 (two fp16 values, 22 significand bits).  Three MMAs per K step,
+// Every fp32 value x travels as two fp16 planes, x ~= hi + lo * 2^-11 (22 significand bits; the producing kernel's
+// epilogue writes them).  Three MMAs per K step,
 //     acc0 += Ah * Bh            acc1 += Ah * Bl + Al * Bh          result = acc0 + acc1 * 2^-11
-// with both fp32 accumulators living in TMEM (2 x 128 columns).  The dropped Al * Bl term is 2^-22 relative.
+// with both fp32 accumulators living in TMEM (2 x 64 columns).  The dropped Al * Bl term is 2^-22 relative.
 //
-// One CTA = 128 threads = one 128 x 128 output tile.  Per 64-wide K chunk the CTA stages A (fp32 -> split fp16, done
-// in-kernel) and B (pre-split fp16 weights, or fp32 activations for the assignment matrix) into shared memory in the
-// UMMA interleaved K-major canonical layout (tc.cuh), one elected thread issues the 12 tcgen05.mma, tcgen05.commit
-// signals an mbarrier, and after the last chunk every warp drains its 32 TMEM lanes with tcgen05.ld for the epilogue.
-// 64 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap staging with the tensor pipe.
+// One CTA = 128 threads = one 128 x 64 output tile.  Operands are already fp16, so staging is pure 16-byte cp.async
+// traffic into the UMMA interleaved K-major canonical layout (tc.cuh), double-buffered: the copies for K chunk k+1 are in
+// flight while the tensor core works on chunk k.  One elected thread issues the 12 tcgen05.mma per chunk; tcgen05.commit
+// arrives on the stage's mbarrier, which is what frees the stage for the chunk after next.  The epilogue drains TMEM with
+// tcgen05.ld, transposes each warp's 32 x 32 block through shared memory so that global traffic is 128-byte coalesced,
+// applies bias / scale / residual and writes fp32 and/or split-fp16 outputs (row-major for the next GEMM, head-major for
+// the attention kernel).  96 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM.
 #pragma once
 #include "common.cuh"
 #include "tc.cuh"
 
+struct GemmTcProblem {  // per-image part: both images of a pair share weights, shapes and epilogue, so they share a launch
+  const __half *A1h, *A1l;  // [M][lda1] fp16 planes of the first K segment
+  const __half *A2h, *A2l;  // optional second K segment (torch.cat([x, msg], -1) without materialising the concat)
+  const float* resid;       // [M][ldr] fp32 or null, added after bias / scale
+  float* C;                 // optional fp32 output, row-major [M][ldc]
+  __half *Ch, *Cl;          // optional split output planes
+  int M;
+};
 struct GemmTcArgs {
-  const float* A1;
+  GemmTcProblem p[2];  // blockIdx.z selects; p[1].M == 0 for a single problem
   int lda1;
   int K1;
-  const float* A2;
   int lda2;
   int K2;
-  const __half* Bh;  // [N][K] fp16 hi   (B_IS_F32 == false)
-  const __half* Bl;  // [N][K] fp16 lo * 2^11
-  const float* Bf;   // [N][K] fp32      (B_IS_F32 == true)
+  const __half *Bh, *Bl;  // [N][ldb] fp16 planes (nn.Linear weight layout: K contiguous)
   int ldb;
-  float* C;
-  int ldc;
-  int M;
   int N;
-  const float* bias;
-  const float* resid;
+  const float* bias;  // [N] or null
   int ldr;
   float scale;
-  int head_major;
-  int* err_flag;  // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
+  int ldc;
+  int ldch;        // row-major leading dimension of Ch / Cl (ignored when head_major)
+  int head_major;  // 1: Ch / Cl (and C) are written as [N/64][M][64] (attention head layout)
+  int* err_flag;   // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
 };
 
-constexpr int TC_M = 128, TC_N = 128, TC_K = 64;
-constexpr int TC_TILE_BYTES = TC_M * TC_K * 2;  // one fp16 operand tile: 16 KB
-constexpr size_t TC_GEMM_SMEM = 4 * TC_TILE_BYTES + 1024;
+constexpr int TC_M = 128, TC_N = 64, TC_K = 64, TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_M * TC_K * 2;  // one fp16 A plane tile: 16 KB
+constexpr int TC_B_BYTES = TC_N * TC_K * 2;  // one fp16 B plane tile: 8 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
+constexpr size_t TC_GEMM_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024;
 
-template <bool B_IS_F32>
-__global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g) {
+static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
   extern __shared__ __align__(1024) unsigned char tsm[];
-  unsigned char* sAh = tsm;
-  unsigned char* sAl = sAh + TC_TILE_BYTES;
-  unsigned char* sBh = sAl + TC_TILE_BYTES;
-  unsigned char* sBl = sBh + TC_TILE_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sBl + TC_TILE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + TC_STAGES * TC_STAGE_BYTES);  // bar[s]: MMAs reading stage s done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + TC_STAGES);
 
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const GemmTcProblem& pb = g.p[blockIdx.z];
+  const int M = pb.M;
   const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * TC_N;
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  if (m0 >= M) return;  // uniform; before any allocation / barrier
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 2 * TC_N);
   if (t == 0) {
-    tc::mbar_init(bar, 1);
+    for (int s = 0; s < TC_STAGES; ++s) tc::mbar_init(&bar[s], 1);
     tc::fence_mbar_init();
   }
+  const uint32_t smem0 = tc::smem_u32(tsm);
+  const int K = g.K1 + g.K2, nk = K / TC_K;
+
+  auto load_chunk = [&](int kc, int stage) {
+    const int k0 = kc * TC_K;
+    const __half *ah, *al;
+    int lda, ka;
+    if (k0 < g.K1) ah = pb.A1h, al = pb.A1l, lda = g.lda1, ka = k0;
+    else ah = pb.A2h, al = pb.A2l, lda = g.lda2, ka = k0 - g.K1;
+    const uint32_t sA = smem0 + stage * TC_STAGE_BYTES, sB = sA + 2 * TC_A_BYTES;
+    // A: 128 rows x 8 chunks.  Lane pairs read the two 16-byte halves of one 32-byte sector (no L2 over-fetch); the
+    // 16 rows a warp touches per instruction land in distinct banks except for the pair's 2-way overlap.
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * 128 + t;            // 0 .. 1023 = 128 rows x 8 chunks
+      const int c = (idx & 1) + 2 * (idx >> 8);  // chunk: pair index within the sector, 4 sector columns over i
+      const int r = (idx >> 1) & 127;
+      const int m = m0 + r;
+      const uint32_t okb = m < M ? 16u : 0u;
+      const size_t src = (size_t)(m < M ? m : 0) * lda + ka + c * 8;
+      const uint32_t off = tc::canon_off(r, c, TC_M);
+      tc::cp_async16(sA + off, ah + src, okb);
+      tc::cp_async16(sA + TC_A_BYTES + off, al + src, okb);
+    }
+    // B: 64 rows x 8 chunks over 128 threads, same pairing
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 128 + t;  // 0 .. 511
+      const int c = (idx & 1) + 2 * (idx >> 7);
+      const int r = (idx >> 1) & 63;
+      const int n = n0 + r;
+      const uint32_t okb = n < g.N ? 16u : 0u;
+      const size_t src = (size_t)(n < g.N ? n : 0) * g.ldb + k0 + c * 8;
+      const uint32_t off = tc::canon_off(r, c, TC_N);
+      tc::cp_async16(sB + off, g.Bh + src, okb);
+      tc::cp_async16(sB + TC_B_BYTES + off, g.Bl + src, okb);
+    }
+  };
+
+  load_chunk(0, 0);
+  tc::cp_async_commit();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = tc::idesc_f16(TC_M, TC_N);
-  const uint32_t lbo = (TC_M / 8) * 128;  // 2048 B between K chunks
-  const int K = g.K1 + g.K2;
-  uint32_t phase = 0;
+  const uint32_t lboA = (TC_M / 8) * 128, lboB = (TC_N / 8) * 128;
   bool ok = true;
 
-  for (int k0 = 0; k0 < K; k0 += TC_K) {
-    // ---- stage A: thread t owns row m0 + t ------------------------------------------------------------------
-    {
-      const int m = m0 + t;
-      const float* src = nullptr;
-      if (m < g.M) src = (k0 < g.K1) ? g.A1 + (size_t)m * g.lda1 + k0 : g.A2 + (size_t)m * g.lda2 + (k0 - g.K1);
-#pragma unroll
-      for (int c = 0; c < TC_K / 8; ++c) {
-        float x[8];
-        if (src) {
-          float4 a = *reinterpret_cast<const float4*>(src + c * 8), b = *reinterpret_cast<const float4*>(src + c * 8 + 4);
-          x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = 0.f;
-        }
-        uint4 hi, lo;
-        tc::split8(x, hi, lo);
-        const uint32_t off = tc::canon_off(t, c, TC_M);
-        *reinterpret_cast<uint4*>(sAh + off) = hi;
-        *reinterpret_cast<uint4*>(sAl + off) = lo;
-      }
+  for (int kc = 0; kc < nk; ++kc) {
+    const int stage = kc & 1;
+    if (kc + 1 < nk) {
+      // stage (kc + 1) & 1 was last read by the MMAs of chunk kc - 1: wait for their commit before overwriting it
+      if (kc >= 1) ok = tc::mbar_wait(&bar[(kc + 1) & 1], ((kc - 1) >> 1) & 1) && ok;
+      load_chunk(kc + 1, (kc + 1) & 1);
     }
-    // ---- stage B: thread t owns row n0 + t --------------------------------------------------------------------
-    {
-      const int n = n0 + t;
-#pragma unroll
-      for (int c = 0; c < TC_K / 8; ++c) {
-        uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if (n < g.N) {
-          if (B_IS_F32) {
-            const float* src = g.Bf + (size_t)n * g.ldb + k0 + c * 8;
-            float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-            float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            tc::split8(x, hi, lo);
-          } else {
-            hi = *reinterpret_cast<const uint4*>(g.Bh + (size_t)n * g.ldb + k0 + c * 8);
-            lo = *reinterpret_cast<const uint4*>(g.Bl + (size_t)n * g.ldb + k0 + c * 8);
-          }
-        }
-        const uint32_t off = tc::canon_off(t, c, TC_N);
-        *reinterpret_cast<uint4*>(sBh + off) = hi;
-        *reinterpret_cast<uint4*>(sBl + off) = lo;
-      }
-    }
-    tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc::cp_async_commit();
+    tc::cp_async_wait<1>();  // chunk kc has landed (only the newest group may still be in flight)
+    tc::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
       tc::fence_after_sync();
-      const uint32_t aH = tc::smem_u32(sAh), aL = tc::smem_u32(sAl), bH = tc::smem_u32(sBh), bL = tc::smem_u32(sBl);
+      const uint32_t aH = smem0 + stage * TC_STAGE_BYTES, aL = aH + TC_A_BYTES, bH = aH + 2 * TC_A_BYTES, bL = bH + TC_B_BYTES;
 #pragma unroll
       for (int s = 0; s < TC_K / 16; ++s) {
-        const uint32_t ko = 2 * s * lbo;
-        const uint64_t dAh = tc::smem_desc(aH + ko, lbo), dAl = tc::smem_desc(aL + ko, lbo);
-        const uint64_t dBh = tc::smem_desc(bH + ko, lbo), dBl = tc::smem_desc(bL + ko, lbo);
-        const uint32_t first = (k0 == 0 && s == 0) ? 0u : 1u;
+        const uint64_t dAh = tc::smem_desc(aH + 2 * s * lboA, lboA), dAl = tc::smem_desc(aL + 2 * s * lboA, lboA);
+        const uint64_t dBh = tc::smem_desc(bH + 2 * s * lboB, lboB), dBl = tc::smem_desc(bL + 2 * s * lboB, lboB);
+        const uint32_t first = (kc == 0 && s == 0) ? 0u : 1u;
         tc::umma_f16(tmem, dAh, dBh, idesc, first);         // acc0 (+)= Ah Bh
         tc::umma_f16(tmem + TC_N, dAh, dBl, idesc, first);  // acc1 (+)= Ah Bl
         tc::umma_f16(tmem + TC_N, dAl, dBh, idesc, 1u);     // acc1  += Al Bh
       }
-      tc::umma_commit(bar);
+      tc::umma_commit(&bar[stage]);
     }
-    ok = tc::mbar_wait(bar, phase) && ok;  // MMAs of this chunk done: smem may be overwritten
-    phase ^= 1;
   }
+  // all MMAs complete when the last chunk's commit arrives (commits are ordered)
+  ok = tc::mbar_wait(&bar[(nk - 1) & 1], ((nk - 1) >> 1) & 1) && ok;
+  tc::cp_async_wait<0>();
   tc::fence_after_sync();
   if (!ok && g.err_flag) *g.err_flag = 1;
+  __syncthreads();  // every warp is past its waits before the operand tiles are reused as scratch
 
-  // ---- epilogue: thread t = accumulator row (TMEM lane) t ---------------------------------------------------------
-  const int m = m0 + t;
+  // ---- epilogue ---------------------------------------------------------------------------------------------------
+  float* scratch = reinterpret_cast<float*>(tsm) + warp * (32 * 33);
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
   for (int cc = 0; cc < TC_N / 32; ++cc) {
-    float a0[32], a1[32];
-    tc::tmem_ld32(lane_base + cc * 32, a0);
-    tc::tmem_ld32(lane_base + TC_N + cc * 32, a1);
-    if (m < g.M) {
+    if (n0 + cc * 32 >= g.N) break;  // uniform
+    {
+      float a0[32], a1[32];
+      tc::tmem_ld32(lane_base + cc * 32, a0);
+      tc::tmem_ld32(lane_base + TC_N + cc * 32, a1);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + cc * 32 + j;
-        if (n < g.N) {
-          float v = fmaf(a1[j], tc::LO_INV, a0[j]);
-          if (g.bias) v += g.bias[n];
-          v *= g.scale;
-          if (g.resid) v += g.resid[(size_t)m * g.ldr + n];
-          if (g.head_major)
-            g.C[((size_t)(n >> 6) * g.M + m) * 64 + (n & 63)] = v;
-          else
-            g.C[(size_t)m * g.ldc + n] = v;
-        }
+      for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = fmaf(a1[j], tc::LO_INV, a0[j]);
+    }
+    __syncwarp();
+    const int n = n0 + cc * 32 + lane;
+    const float bn = (g.bias && n < g.N) ? g.bias[n] : 0.f;
+    float rv[32];  // residual rows fetched up front: 32 independent coalesced loads in flight instead of a serial chain
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int m = m0 + warp * 32 + r;
+      rv[r] = (pb.resid && m < M && n < g.N) ? pb.resid[(size_t)m * g.ldr + n] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int m = m0 + warp * 32 + r;
+      if (m >= M || n >= g.N) continue;
+      float v = (scratch[r * 33 + lane] + bn) * g.scale + rv[r];
+      const size_t oh = ((size_t)(n >> 6) * M + m) * 64 + (n & 63);
+      if (pb.C) pb.C[g.head_major ? oh : (size_t)m * g.ldc + n] = v;
+      if (pb.Ch) {
+        __half hh, ll;
+        tc::split_h(v, hh, ll);
+        const size_t o = g.head_major ? oh : (size_t)m * g.ldch + n;
+        pb.Ch[o] = hh;
+        pb.Cl[o] = ll;
       }
     }
+    __syncwarp();
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem, 2 * TC_N);
 }
 
-// fp32 [rows][cols] -> fp16 hi / lo*2^11 copies (weights, once at load time)
+// fp32 -> fp16 hi / lo * 2^11 planes (weights once at load time; network inputs once per call)
 static __global__ void k_split_f32(const float* __restrict__ x, size_t n, __half* __restrict__ hi, __half* __restrict__ lo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

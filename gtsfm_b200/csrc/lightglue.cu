@@ -35,9 +35,10 @@ struct ConfW {
 }  // namespace
 
 struct LgSide {  // per-image workspace
-  DevBuf x[2], qkv, q, k, v, ctx, msg, h, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, amax, aidx;
-  int cur = 0;  // which of x / cs / sn / ind is live
+  DevBuf x[2], xs[2], qkv, q, k, v, ctx, msg, h, hs, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, amax, aidx;
+  int cur = 0;  // which of x / xs / cs / sn / ind is live
   int n = 0;
+  int cap = 0;  // rows allocated; split-plane buffers keep their lo plane at +cap * width halves whatever n shrinks to
 };
 
 struct LightGlueState {
@@ -63,7 +64,7 @@ void lg_destroy(b2_context* ctx) {
   s->wblob_l.release();
   s->errflag.release();
   for (auto& sd : s->side) {
-    DevBuf* bufs[] = {&sd.x[0], &sd.x[1], &sd.qkv, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.cs[0], &sd.cs[1],
+    DevBuf* bufs[] = {&sd.x[0], &sd.x[1], &sd.xs[0], &sd.xs[1], &sd.hs, &sd.qkv, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.cs[0], &sd.cs[1],
                       &sd.sn[0], &sd.sn[1], &sd.ind[0], &sd.ind[1], &sd.conf, &sd.mat, &sd.src, &sd.md, &sd.rmax,
                       &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
     for (DevBuf* b : bufs) b->release();
@@ -115,10 +116,12 @@ __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp
   for (int i = threadIdx.x; i < n; i += blockDim.x) ind[i] = i;
 }
 
-// qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64].
+// qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64],
+// either as fp32 (SIMT attention) or split into fp16 hi / lo planes (tcgen05 attention; plane stride = 4*N*64 halves).
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict__ qkv, const float* __restrict__ cs,
-                                                          const float* __restrict__ sn, int n, float* __restrict__ q,
-                                                          float* __restrict__ k, float* __restrict__ v) {
+                                                          const float* __restrict__ sn, int n, size_t plane,
+                                                          void* __restrict__ qo, void* __restrict__ ko, void* __restrict__ vo) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n * 4 * 32 pairs
   if (i >= n * 128) return;
   int p = i & 31, h = (i >> 5) & 3, r = i >> 7;
@@ -127,17 +130,30 @@ __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict
   float c = cs[r * 32 + p], s = sn[r * 32 + p];
   size_t o = ((size_t)h * n + r) * 64 + 2 * p;
   // (t * cos) + (rotate_half(t) * sin), rotate_half: (x1, x2) -> (-x2, x1)
-  q[o] = __fadd_rn(__fmul_rn(q0, c), __fmul_rn(-q1, s));
-  q[o + 1] = __fadd_rn(__fmul_rn(q1, c), __fmul_rn(q0, s));
-  k[o] = __fadd_rn(__fmul_rn(k0, c), __fmul_rn(-k1, s));
-  k[o + 1] = __fadd_rn(__fmul_rn(k1, c), __fmul_rn(k0, s));
-  v[o] = v0;
-  v[o + 1] = v1;
+  const float qa = __fadd_rn(__fmul_rn(q0, c), __fmul_rn(-q1, s)), qb = __fadd_rn(__fmul_rn(q1, c), __fmul_rn(q0, s));
+  const float ka = __fadd_rn(__fmul_rn(k0, c), __fmul_rn(-k1, s)), kb = __fadd_rn(__fmul_rn(k1, c), __fmul_rn(k0, s));
+  if (SPLIT) {
+    __half* outs[3] = {static_cast<__half*>(qo), static_cast<__half*>(ko), static_cast<__half*>(vo)};
+    const float va[3] = {qa, ka, v0}, vb[3] = {qb, kb, v1};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      __half ha, la, hb, lb;
+      tc::split_h(va[j], ha, la);
+      tc::split_h(vb[j], hb, lb);
+      *reinterpret_cast<__half2*>(outs[j] + o) = __halves2half2(ha, hb);
+      *reinterpret_cast<__half2*>(outs[j] + plane + o) = __halves2half2(la, lb);
+    }
+  } else {
+    float *q = static_cast<float*>(qo), *k = static_cast<float*>(ko), *v = static_cast<float*>(vo);
+    q[o] = qa, q[o + 1] = qb, k[o] = ka, k[o + 1] = kb, v[o] = v0, v[o + 1] = v1;
+  }
 }
 
 // LayerNorm(512, eps 1e-5, affine) + exact GELU in place (lightglue.py:152-157). one warp per row.
+// When `hi` is given the result is written as split fp16 planes (the next GEMM's A operand) instead of in place.
 __global__ void __launch_bounds__(256) k_lg_ln_gelu(float* __restrict__ h, int n, const float* __restrict__ g,
-                                                     const float* __restrict__ b) {
+                                                     const float* __restrict__ b, __half* __restrict__ hi,
+                                                     __half* __restrict__ lo) {
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= n) return;
   float4* row = reinterpret_cast<float4*>(h + (size_t)r * 512);
@@ -164,7 +180,15 @@ __global__ void __launch_bounds__(256) k_lg_ln_gelu(float* __restrict__ h, int n
                   (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) e[j] = 0.5f * e[j] * (1.0f + erff(e[j] * 0.70710678118654752440f));
-    row[lane + 32 * i] = make_float4(e[0], e[1], e[2], e[3]);
+    if (hi) {
+      uint32_t h01, l01, h23, l23;
+      tc::split2(e[0], e[1], h01, l01);
+      tc::split2(e[2], e[3], h23, l23);
+      *reinterpret_cast<uint2*>(hi + (size_t)r * 512 + c0) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(lo + (size_t)r * 512 + c0) = make_uint2(l01, l23);
+    } else {
+      row[lane + 32 * i] = make_float4(e[0], e[1], e[2], e[3]);
+    }
   }
 }
 
@@ -249,7 +273,8 @@ __global__ void __launch_bounds__(256) k_lg_gather(const int* __restrict__ src, 
                                                     const float* __restrict__ x, const float* __restrict__ cs,
                                                     const float* __restrict__ sn, const int* __restrict__ ind,
                                                     float* __restrict__ x2, float* __restrict__ cs2, float* __restrict__ sn2,
-                                                    int* __restrict__ ind2) {
+                                                    int* __restrict__ ind2, const __half* __restrict__ ph, size_t pstride,
+                                                    __half* __restrict__ ph2, size_t pstride2) {
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= *cnt) return;
   int s = src[r];
@@ -260,6 +285,10 @@ __global__ void __launch_bounds__(256) k_lg_gather(const int* __restrict__ src, 
   cs2[r * 32 + lane] = cs[s * 32 + lane];
   sn2[r * 32 + lane] = sn[s * 32 + lane];
   if (lane == 0) ind2[r] = ind[s];
+  if (ph) {  // split planes of x travel with it: 256 halves = 32 lanes x 16 bytes per plane
+    reinterpret_cast<uint4*>(ph2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(ph + (size_t)s * 256)[lane];
+    reinterpret_cast<uint4*>(ph2 + pstride2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(ph + pstride + (size_t)s * 256)[lane];
+  }
 }
 
 // log-softmax statistics of sim rows: max and log(sum(exp(x - max)))  (F.log_softmax, lightglue.py:271). warp per row.
@@ -276,17 +305,35 @@ __global__ void __launch_bounds__(256) k_lg_row_stats(const float* __restrict__ 
   s = warp_sum(s);
   if (lane == 0) rmax[r] = mx, rlog[r] = logf(s);
 }
-// same along columns (log_softmax of sim^T, :272): thread per column, coalesced across columns; rows split over
-// blockIdx.y slabs would need a second pass, so one thread walks all rows (m <= 5000).
-__global__ void __launch_bounds__(128) k_lg_col_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ cmax,
+// same along columns (log_softmax of sim^T, :272): a block owns 32 columns; its 8 warps stride over the rows (each row
+// access is one coalesced 128-byte line), keeping an online (max, sum) pair that is merged across warps at the end.
+__global__ void __launch_bounds__(256) k_lg_col_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ cmax,
                                                        float* __restrict__ clog) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  float mx = -INFINITY;
-  for (int i = 0; i < m; ++i) mx = fmaxf(mx, sim[(size_t)i * n + j]);
-  float s = 0.f;
-  for (int i = 0; i < m; ++i) s += expf(sim[(size_t)i * n + j] - mx);
-  cmax[j] = mx, clog[j] = logf(s);
+  __shared__ float sm[8][32], ss[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float mx = -INFINITY, s = 0.f;
+  if (j < n) {
+    for (int i = warp; i < m; i += 8) {
+      float x = sim[(size_t)i * n + j];
+      if (x > mx) {
+        s = s * expf(mx - x) + 1.0f;
+        mx = x;
+      } else {
+        s += expf(x - mx);
+      }
+    }
+  }
+  sm[warp][lane] = mx, ss[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+    float M = sm[0][lane];
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, sm[w][lane]);
+    float S = 0.f;
+    for (int w = 0; w < 8; ++w)
+      if (ss[w][lane] > 0.f) S += ss[w][lane] * expf(sm[w][lane] - M);
+    cmax[j] = M, clog[j] = logf(S);
+  }
 }
 
 __device__ __forceinline__ float logsigmoid(float z) {  // F.logsigmoid: min(z, 0) - log1p(exp(-|z|))
@@ -319,22 +366,35 @@ __global__ void __launch_bounds__(256) k_lg_row_argmax(const float* __restrict__
   }
   if (lane == 0) best[r] = bv, arg[r] = bi;
 }
-__global__ void __launch_bounds__(128) k_lg_col_argmax(const float* __restrict__ sim, int m, int n,
+__global__ void __launch_bounds__(256) k_lg_col_argmax(const float* __restrict__ sim, int m, int n,
                                                         const float* __restrict__ rmax, const float* __restrict__ rlog,
                                                         const float* __restrict__ cmax, const float* __restrict__ clog,
                                                         const float* __restrict__ z0, const float* __restrict__ z1,
                                                         int* __restrict__ arg) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const float cm = cmax[j], cl = clog[j], l1 = logsigmoid(z1[j]);
+  __shared__ float sv[8][32];
+  __shared__ int si[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   float bv = -INFINITY;
-  int bi = 0;
-  for (int i = 0; i < m; ++i) {
-    float x = sim[(size_t)i * n + j];
-    float sc = (((x - rmax[i]) - rlog[i]) + ((x - cm) - cl)) + (logsigmoid(z0[i]) + l1);
-    if (sc > bv) bv = sc, bi = i;
+  int bi = 0x7fffffff;
+  if (j < n) {
+    const float cm = cmax[j], cl = clog[j], l1 = logsigmoid(z1[j]);
+    for (int i = warp; i < m; i += 8) {
+      float x = sim[(size_t)i * n + j];
+      float sc = (((x - rmax[i]) - rlog[i]) + ((x - cm) - cl)) + (logsigmoid(z0[i]) + l1);
+      if (sc > bv) bv = sc, bi = i;  // rows ascend within a warp: first maximum kept
+    }
   }
-  arg[j] = bi;
+  sv[warp][lane] = bv, si[warp][lane] = bi;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+    for (int w = 1; w < 8; ++w) {
+      float ov = sv[w][lane];
+      int oi = si[w][lane];
+      if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+    }
+    arg[j] = bi == 0x7fffffff ? 0 : bi;
+  }
 }
 
 // filter_matches (:302-318) + index mapping through ind0 / ind1 (:598-602) + ordered compaction (single block).
@@ -457,8 +517,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
             s->wblob_h.as<__half>(), s->wblob_l.as<__half>());
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaDeviceSynchronize());
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
   {
     const char* e = getenv("B2_FORCE_SIMT");
@@ -471,35 +530,112 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   return B2_OK;
 }
 
-// GEMM dispatch: tcgen05 split-fp16 kernel (weights pre-split, or an fp32 B operand converted in-kernel), or the
-// SIMT fp32 kernel when forced.  `b_is_weight` says g.B points into the weight blob.
-static int lg_gemm(b2_context* ctx, cudaStream_t st, LightGlueState* s, const GemmArgs& g, bool b_is_weight) {
-  if (!s->use_tc || ((g.K1 + g.K2) % TC_K) != 0 || (g.K1 % TC_K) != 0) return launch_gemm(ctx, st, g);
-  if (g.M <= 0 || g.N <= 0) return B2_OK;
-  GemmTcArgs t{};
-  t.A1 = g.A1, t.lda1 = g.lda1, t.K1 = g.K1, t.A2 = g.A2, t.lda2 = g.lda2, t.K2 = g.K2, t.ldb = g.ldb;
-  t.C = g.C, t.ldc = g.ldc, t.M = g.M, t.N = g.N, t.bias = g.bias, t.resid = g.resid, t.ldr = g.ldr, t.scale = g.scale;
-  t.head_major = g.head_major, t.err_flag = s->errflag.as<int>();
-  dim3 grid(cdiv(g.N, TC_N), cdiv(g.M, TC_M));
-  b2_prof_work(ctx, "k_gemm_tc", 2.0 * g.M * g.N * (g.K1 + g.K2));
-  if (b_is_weight) {
-    const size_t off = (size_t)(g.B - s->wblob.as<float>());
-    t.Bh = s->wblob_h.as<__half>() + off, t.Bl = s->wblob_l.as<__half>() + off;
-    B2_LAUNCH(ctx, k_gemm_tc<false>, grid, 128, TC_GEMM_SMEM, st, t);
-  } else {
-    t.Bf = g.B;
-    B2_LAUNCH(ctx, k_gemm_tc<true>, grid, 128, TC_GEMM_SMEM, st, t);
+struct Pl {  // split-fp16 planes of an activation
+  __half* hi;
+  __half* lo;
+};
+static inline Pl planes_of(const DevBuf& b, size_t elems) { return {b.as<__half>(), b.as<__half>() + elems}; }
+
+// One linear / GEMM call site, expressed for both execution paths: fp32 views feed the exact-fp32 SIMT kernel,
+// split-fp16 plane views feed the tcgen05 kernel.
+struct LinArgs {
+  const float* a1f = nullptr;
+  Pl a1p{nullptr, nullptr};
+  int lda1 = 0, K1 = 0;
+  const float* a2f = nullptr;
+  Pl a2p{nullptr, nullptr};
+  int lda2 = 0, K2 = 0;
+  const float* w = nullptr;   // weight inside the blob (B operand), or
+  const float* bf = nullptr;  // an fp32 activation B operand with
+  Pl bp{nullptr, nullptr};    // its planes
+  int ldb = 0;
+  const float* bias = nullptr;
+  float scale = 1.f;
+  const float* resid = nullptr;
+  int ldr = 0;
+  float* cf = nullptr;  // fp32 output (always written on the SIMT path; on the tcgen05 path only if tc_want_f32)
+  int ldc = 0;
+  Pl cp{nullptr, nullptr};  // plane output (tcgen05 path)
+  int ldch = 0;
+  int head_major = 0;
+  bool tc_want_f32 = false;
+  int M = 0, N = 0;
+};
+
+// `b` (optional) is the same linear applied to the other image of the pair: same weights, shapes and epilogue, so the
+// tcgen05 path runs both as one launch (blockIdx.z).
+static int lg_linear(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LinArgs& a, const LinArgs* b = nullptr) {
+  if (!s->use_tc) {
+    const LinArgs* both[2] = {&a, b};
+    for (int i = 0; i < 2; ++i) {
+      if (!both[i] || both[i]->M <= 0 || both[i]->N <= 0) continue;
+      const LinArgs& x = *both[i];
+      GemmArgs g{};
+      g.A1 = x.a1f, g.lda1 = x.lda1, g.K1 = x.K1, g.A2 = x.a2f, g.lda2 = x.lda2, g.K2 = x.K2;
+      g.B = x.w ? x.w : x.bf, g.ldb = x.ldb, g.C = x.cf, g.ldc = x.ldc, g.M = x.M, g.N = x.N;
+      g.bias = x.bias, g.resid = x.resid, g.ldr = x.ldr, g.scale = x.scale, g.head_major = x.head_major;
+      int rc = launch_gemm(ctx, st, g);
+      if (rc) return rc;
+    }
+    return B2_OK;
   }
+  if (a.N <= 0 || (a.M <= 0 && (!b || b->M <= 0))) return B2_OK;
+  GemmTcArgs t{};
+  const LinArgs* both[2] = {&a, b};
+  int maxM = 0;
+  double work = 0.0;
+  for (int i = 0; i < 2; ++i) {
+    if (!both[i]) continue;
+    const LinArgs& x = *both[i];
+    GemmTcProblem& q = t.p[i];
+    q.A1h = x.a1p.hi, q.A1l = x.a1p.lo, q.A2h = x.a2p.hi, q.A2l = x.a2p.lo, q.resid = x.resid;
+    q.C = x.tc_want_f32 ? x.cf : nullptr, q.Ch = x.cp.hi, q.Cl = x.cp.lo, q.M = x.M;
+    maxM = x.M > maxM ? x.M : maxM;
+    work += 2.0 * x.M * x.N * (x.K1 + x.K2);
+  }
+  t.lda1 = a.lda1, t.K1 = a.K1, t.lda2 = a.lda2, t.K2 = a.K2;
+  if (a.w) {
+    const size_t off = (size_t)(a.w - s->wblob.as<float>());
+    t.Bh = s->wblob_h.as<__half>() + off, t.Bl = s->wblob_l.as<__half>() + off;
+  } else {
+    t.Bh = a.bp.hi, t.Bl = a.bp.lo;
+  }
+  t.ldb = a.ldb, t.N = a.N, t.bias = a.bias, t.ldr = a.ldr, t.scale = a.scale, t.ldc = a.ldc, t.ldch = a.ldch;
+  t.head_major = a.head_major, t.err_flag = s->errflag.as<int>();
+  dim3 grid(cdiv(a.N, TC_N), cdiv(maxM, TC_M), b ? 2 : 1);
+  b2_prof_work(ctx, "k_gemm_tc", work);
+  B2_LAUNCH(ctx, k_gemm_tc, grid, 128, TC_GEMM_SMEM, st, t);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
 }
 
-static int lg_flash(b2_context* ctx, cudaStream_t st, LightGlueState* s, const float* Q, const float* K, const float* V,
-                    float* O, int Nq, int Nk, float scale) {
-  if (!s->use_tc) return launch_flash(ctx, st, Q, K, V, O, Nq, Nk, scale);
-  if (Nq <= 0) return B2_OK;
-  b2_prof_work(ctx, "k_flash_tc", 4.0 * 2.0 * 2.0 * (double)Nq * Nk * 64);  // 4 heads x (QK^T + PV) x 2 FLOP/MAC
-  B2_LAUNCH(ctx, k_flash_tc, dim3(cdiv(Nq, AT_Q), 4), 128, AT_SMEM, st, Q, K, V, O, Nq, Nk, scale, s->errflag.as<int>());
+// One launch, two attention problems.  tcgen05 path: q / k / v / o buffers hold split fp16 planes (hi, then lo at + N * 256).
+struct FlashJob {
+  const DevBuf *q, *k, *v, *o;
+  int nq, nk;
+  int capq, capk;  // allocated rows of the query-side / key-side buffers (lo plane offset = cap * 256 halves)
+};
+static int lg_flash2(b2_context* ctx, cudaStream_t st, LightGlueState* s, const FlashJob& a, const FlashJob& b, float scale) {
+  if (!s->use_tc) {
+    int rc;
+    if ((rc = launch_flash(ctx, st, a.q->as<float>(), a.k->as<float>(), a.v->as<float>(), a.o->as<float>(), a.nq, a.nk, scale))) return rc;
+    return launch_flash(ctx, st, b.q->as<float>(), b.k->as<float>(), b.v->as<float>(), b.o->as<float>(), b.nq, b.nk, scale);
+  }
+  AttnArgs args{};
+  const FlashJob* jobs[2] = {&a, &b};
+  for (int i = 0; i < 2; ++i) {
+    const FlashJob& j = *jobs[i];
+    AttnProblem& p = args.p[i];
+    const Pl q = planes_of(*j.q, (size_t)j.capq * 256), k = planes_of(*j.k, (size_t)j.capk * 256), v = planes_of(*j.v, (size_t)j.capk * 256),
+             o = planes_of(*j.o, (size_t)j.capq * 256);
+    p.Qh = q.hi, p.Ql = q.lo, p.Kh = k.hi, p.Kl = k.lo, p.Vh = v.hi, p.Vl = v.lo, p.Oh = o.hi, p.Ol = o.lo;
+    p.Nq = j.nq, p.Nk = j.nk;
+  }
+  args.scale = scale, args.err_flag = s->errflag.as<int>();
+  const int qt = cdiv(a.nq > b.nq ? a.nq : b.nq, AT_Q);
+  if (qt <= 0) return B2_OK;
+  b2_prof_work(ctx, "k_flash_tc", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));  // 4 heads x (QK^T + PV) x 2 FLOP/MAC
+  B2_LAUNCH(ctx, k_flash_tc, dim3(qt, 4, 2), 128, AT_SMEM, st, args);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
 }
@@ -508,6 +644,7 @@ static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
   const size_t N = (size_t)(n > 0 ? n : 1);
   for (int i = 0; i < 2; ++i) {
     B2_CUDA(ctx, sd.x[i].ensure(N * 256 * 4));
+    B2_CUDA(ctx, sd.xs[i].ensure(N * 256 * 4));
     B2_CUDA(ctx, sd.cs[i].ensure(N * 32 * 4));
     B2_CUDA(ctx, sd.sn[i].ensure(N * 32 * 4));
     B2_CUDA(ctx, sd.ind[i].ensure(N * 4));
@@ -519,68 +656,100 @@ static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
   B2_CUDA(ctx, sd.ctx.ensure(N * 256 * 4));
   B2_CUDA(ctx, sd.msg.ensure(N * 256 * 4));
   B2_CUDA(ctx, sd.h.ensure(N * 512 * 4));
+  B2_CUDA(ctx, sd.hs.ensure(N * 512 * 4));
   B2_CUDA(ctx, sd.md.ensure(N * 256 * 4));
   DevBuf* small[] = {&sd.conf, &sd.mat, &sd.src, &sd.rmax, &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
   for (DevBuf* b : small) B2_CUDA(ctx, b->ensure(N * 4));
   sd.cur = 0;
   sd.n = n;
+  sd.cap = n;
   return B2_OK;
 }
 
-// x + ffn(cat[x, msg])  (lightglue.py:152-157,172,228-229): Linear(512,512) -> LN -> GELU -> Linear(512,256) + x
-static int lg_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, LgSide& sd, const float* w0, const float* b0, const float* lng,
-                  const float* lnb, const float* w3, const float* b3) {
-  const int n = sd.n;
-  float* x = sd.x[sd.cur].as<float>();
-  GemmArgs g = gemm_linear(x, 256, 256, w0, b0, sd.h.as<float>(), 512, n, 512);
-  g.A2 = sd.msg.as<float>(), g.lda2 = 256, g.K2 = 256, g.ldb = 512;
+// x + ffn(cat[x, msg])  (lightglue.py:152-157,172,228-229): Linear(512,512) -> LN -> GELU -> Linear(512,256) + x, preceded
+// by the attention output projection (out_proj / to_out); both images of the pair go through each GEMM together.
+static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, const float* wout, const float* bout,
+                          const float* w0, const float* b0, const float* lng, const float* lnb, const float* w3, const float* b3) {
   int rc;
-  if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
-  B2_LAUNCH(ctx, k_lg_ln_gelu, cdiv(n, 8), 256, 0, st, sd.h.as<float>(), n, lng, lnb);
-  B2_CHECK_LAUNCH(ctx);
-  GemmArgs g2 = gemm_linear(sd.h.as<float>(), 512, 512, w3, b3, x, 256, n, 256);
-  g2.resid = x, g2.ldr = 256;  // in place: every element is read (as residual) and written by the same thread
-  return lg_gemm(ctx, st, s, g2, true);
+  LinArgs o[2], f0[2], f3[2];
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    const size_t e = (size_t)sd.cap * 256;
+    float* x = sd.x[sd.cur].as<float>();
+    LinArgs& a = o[i];
+    a.a1f = sd.ctx.as<float>(), a.a1p = planes_of(sd.ctx, e), a.lda1 = 256, a.K1 = 256, a.w = wout, a.ldb = 256, a.bias = bout;
+    a.cf = sd.msg.as<float>(), a.ldc = 256, a.cp = planes_of(sd.msg, e), a.ldch = 256, a.M = sd.n, a.N = 256;
+    LinArgs& f = f0[i];
+    f.a1f = x, f.a1p = planes_of(sd.xs[sd.cur], e), f.lda1 = 256, f.K1 = 256;
+    f.a2f = sd.msg.as<float>(), f.a2p = planes_of(sd.msg, e), f.lda2 = 256, f.K2 = 256;
+    f.w = w0, f.ldb = 512, f.bias = b0, f.cf = sd.h.as<float>(), f.ldc = 512, f.tc_want_f32 = true, f.M = sd.n, f.N = 512;
+    LinArgs& c = f3[i];
+    c.a1f = sd.h.as<float>(), c.a1p = planes_of(sd.hs, (size_t)sd.cap * 512), c.lda1 = 512, c.K1 = 512, c.w = w3, c.ldb = 512, c.bias = b3;
+    c.resid = x, c.ldr = 256;  // in place: every element is read (as residual) and written by the same thread
+    c.cf = x, c.ldc = 256, c.tc_want_f32 = true, c.cp = planes_of(sd.xs[sd.cur], e), c.ldch = 256, c.M = sd.n, c.N = 256;
+  }
+  if ((rc = lg_linear(ctx, st, s, o[0], &o[1]))) return rc;
+  if ((rc = lg_linear(ctx, st, s, f0[0], &f0[1]))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    const Pl hs = planes_of(sd.hs, (size_t)sd.cap * 512);
+    B2_LAUNCH(ctx, k_lg_ln_gelu, cdiv(sd.n, 8), 256, 0, st, sd.h.as<float>(), sd.n, lng, lnb, s->use_tc ? hs.hi : (__half*)nullptr,
+              s->use_tc ? hs.lo : (__half*)nullptr);
+    B2_CHECK_LAUNCH(ctx);
+  }
+  return lg_linear(ctx, st, s, f3[0], &f3[1]);
 }
 
-static int lg_self_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer, LgSide& sd) {
+static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
   const SelfW& w = s->sw[layer];
-  const int n = sd.n;
-  float* x = sd.x[sd.cur].as<float>();
   int rc;
-  if ((rc = lg_gemm(ctx, st, s, gemm_linear(x, 256, 256, w.wqkv, w.bqkv, sd.qkv.as<float>(), 768, n, 768), true))) return rc;
-  B2_LAUNCH(ctx, k_lg_split_rotary, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-            sd.sn[sd.cur].as<float>(), n, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>());
-  B2_CHECK_LAUNCH(ctx);
-  if ((rc = lg_flash(ctx, st, s, sd.q.as<float>(), sd.k.as<float>(), sd.v.as<float>(), sd.ctx.as<float>(), n, n, 0.125f))) return rc;
-  if ((rc = lg_gemm(ctx, st, s, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, n, 256), true))) return rc;
-  return lg_ffn(ctx, st, s, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
+  LinArgs q[2];
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    LinArgs& a = q[i];
+    a.a1f = sd.x[sd.cur].as<float>(), a.a1p = planes_of(sd.xs[sd.cur], (size_t)sd.cap * 256), a.lda1 = 256, a.K1 = 256;
+    a.w = w.wqkv, a.ldb = 256, a.bias = w.bqkv, a.cf = sd.qkv.as<float>(), a.ldc = 768, a.tc_want_f32 = true, a.M = sd.n, a.N = 768;
+  }
+  if ((rc = lg_linear(ctx, st, s, q[0], &q[1]))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    LgSide& sd = s->side[i];
+    const int n = sd.n;
+    if (s->use_tc)
+      B2_LAUNCH(ctx, k_lg_split_rotary<true>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
+                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p);
+    else
+      B2_LAUNCH(ctx, k_lg_split_rotary<false>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
+                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p);
+    B2_CHECK_LAUNCH(ctx);
+  }
+  LgSide &a = s->side[0], &b = s->side[1];
+  FlashJob ja{&a.q, &a.k, &a.v, &a.ctx, a.n, a.n, a.cap, a.cap}, jb{&b.q, &b.k, &b.v, &b.ctx, b.n, b.n, b.cap, b.cap};
+  if ((rc = lg_flash2(ctx, st, s, ja, jb, 0.125f))) return rc;
+  return lg_out_and_ffn(ctx, st, s, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
 static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
   const CrossW& w = s->cw[layer];
   int rc;
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    float* x = sd.x[sd.cur].as<float>();
-    GemmArgs g = gemm_linear(x, 256, 256, w.wqk, w.bqk, sd.q.as<float>(), 0, sd.n, 256);
-    g.head_major = 1;
-    if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
-    GemmArgs gv = gemm_linear(x, 256, 256, w.wv, w.bv, sd.v.as<float>(), 0, sd.n, 256);
-    gv.head_major = 1;
-    if ((rc = lg_gemm(ctx, st, s, gv, true))) return rc;
+  for (int which = 0; which < 2; ++which) {  // to_qk -> sd.q, to_v -> sd.v, both head-major [4][n][64]
+    LinArgs p[2];
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
+      const size_t e = (size_t)sd.cap * 256;
+      LinArgs& a = p[i];
+      a.a1f = sd.x[sd.cur].as<float>(), a.a1p = planes_of(sd.xs[sd.cur], e), a.lda1 = 256, a.K1 = 256;
+      a.w = which ? w.wv : w.wqk, a.ldb = 256, a.bias = which ? w.bv : w.bqk;
+      DevBuf& dst = which ? sd.v : sd.q;
+      a.cf = dst.as<float>(), a.cp = planes_of(dst, e), a.head_major = 1, a.M = sd.n, a.N = 256;
+    }
+    if ((rc = lg_linear(ctx, st, s, p[0], &p[1]))) return rc;
   }
   // m0 = softmax(s * qk0 qk1^T) v1 ; m1 = softmax(s * qk1 qk0^T) v0 with s = 64^-0.5 (the reference scales each
-  // operand by 64^-0.25, lightglue.py:216-221)
+  // operand by 64^-0.25, lightglue.py:216-221); both directions in one launch
   LgSide &a = s->side[0], &b = s->side[1];
-  if ((rc = lg_flash(ctx, st, s, a.q.as<float>(), b.q.as<float>(), b.v.as<float>(), a.ctx.as<float>(), a.n, b.n, 0.125f))) return rc;
-  if ((rc = lg_flash(ctx, st, s, b.q.as<float>(), a.q.as<float>(), a.v.as<float>(), b.ctx.as<float>(), b.n, a.n, 0.125f))) return rc;
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    if ((rc = lg_gemm(ctx, st, s, gemm_linear(sd.ctx.as<float>(), 256, 256, w.wout, w.bout, sd.msg.as<float>(), 256, sd.n, 256), true))) return rc;
-    if ((rc = lg_ffn(ctx, st, s, sd, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3))) return rc;
-  }
-  return B2_OK;
+  FlashJob ja{&a.q, &b.q, &b.v, &a.ctx, a.n, b.n, a.cap, b.cap}, jb{&b.q, &a.q, &a.v, &b.ctx, b.n, a.n, b.cap, a.cap};
+  if ((rc = lg_flash2(ctx, st, s, ja, jb, 0.125f))) return rc;
+  return lg_out_and_ffn(ctx, st, s, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
 static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
@@ -599,6 +768,11 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
     LgSide& sd = s->side[i];
     if ((rc = lg_side_alloc(ctx, sd, ns[i]))) return rc;
     B2_CUDA(ctx, cudaMemcpyAsync(sd.x[0].p, descs[i], (size_t)ns[i] * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    if (s->use_tc) {
+      const Pl xp = planes_of(sd.xs[0], (size_t)sd.cap * 256);
+      B2_LAUNCH(ctx, k_split_f32, (unsigned)cdiv(ns[i] * 256, 256), 256, 0, st, descs[i], (size_t)ns[i] * 256, xp.hi, xp.lo);
+      B2_CHECK_LAUNCH(ctx);
+    }
     B2_LAUNCH(ctx, k_lg_posenc, 1, 1024, 0, st, kps[i], ns[i], s->wr, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>());
     B2_CHECK_LAUNCH(ctx);
   }
@@ -610,8 +784,7 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
   for (layer = 0; layer < LG_LAYERS; ++layer) {
     LgSide &a = s->side[0], &b = s->side[1];
     if (a.n == 0 || b.n == 0) break;
-    if ((rc = lg_self_block(ctx, st, s, layer, a))) return rc;
-    if ((rc = lg_self_block(ctx, st, s, layer, b))) return rc;
+    if ((rc = lg_self_layer(ctx, st, s, layer))) return rc;
     if ((rc = lg_cross_block(ctx, st, s, layer))) return rc;
     if (layer == LG_LAYERS - 1) break;
     if (!do_stop && !do_prune) continue;
@@ -633,7 +806,9 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
         int nxt = sd.cur ^ 1;
         B2_LAUNCH(ctx, k_lg_gather, cdiv(sd.n, 8), 256, 0, st, sd.src.as<int>(), counters + 2 + i, x,
                   sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(),
-                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>());
+                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>(),
+                  s->use_tc ? sd.xs[sd.cur].as<__half>() : (const __half*)nullptr, (size_t)sd.cap * 256, sd.xs[nxt].as<__half>(),
+                  (size_t)sd.cap * 256);
         B2_CHECK_LAUNCH(ctx);
       }
     }
@@ -659,25 +834,30 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
   for (int i = 0; i < 2; ++i) {
     LgSide& sd = s->side[i];
     const float* x = sd.x[sd.cur].as<float>();
-    GemmArgs g = gemm_linear(x, 256, 256, aw.wf, aw.bf, sd.md.as<float>(), 256, sd.n, 256);
-    g.scale = 0.25f;  // / 256 ** 0.25
-    if ((rc = lg_gemm(ctx, st, s, g, true))) return rc;
+    LinArgs g;
+    g.a1f = x, g.a1p = planes_of(sd.xs[sd.cur], (size_t)sd.cap * 256), g.lda1 = 256, g.K1 = 256, g.w = aw.wf, g.ldb = 256;
+    g.bias = aw.bf, g.scale = 0.25f;  // / 256 ** 0.25
+    g.cf = sd.md.as<float>(), g.ldc = 256, g.cp = planes_of(sd.md, (size_t)sd.cap * 256), g.ldch = 256, g.M = sd.n, g.N = 256;
+    if ((rc = lg_linear(ctx, st, s, g))) return rc;  // (the two images may stop with different sizes: separate launches)
     B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, (const float*)nullptr, (const float*)nullptr, aw.wm,
               aw.bm, (float*)nullptr, (float*)nullptr, sd.ls.as<float>());
     B2_CHECK_LAUNCH(ctx);
   }
   B2_CUDA(ctx, s->sim.ensure((size_t)a.n * b.n * 4));
-  GemmArgs gs = gemm_linear(a.md.as<float>(), 256, 256, b.md.as<float>(), nullptr, s->sim.as<float>(), b.n, a.n, b.n);
-  if ((rc = lg_gemm(ctx, st, s, gs, false))) return rc;
+  LinArgs gs;
+  gs.a1f = a.md.as<float>(), gs.a1p = planes_of(a.md, (size_t)a.cap * 256), gs.lda1 = 256, gs.K1 = 256;
+  gs.bf = b.md.as<float>(), gs.bp = planes_of(b.md, (size_t)b.cap * 256), gs.ldb = 256;
+  gs.cf = s->sim.as<float>(), gs.ldc = b.n, gs.tc_want_f32 = true, gs.M = a.n, gs.N = b.n;
+  if ((rc = lg_linear(ctx, st, s, gs))) return rc;
   const float* sim = s->sim.as<float>();
   B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>());
   B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 128), 128, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>());
+  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 32), 256, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>());
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_lg_row_argmax, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
             b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
   B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 128), 128, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
             b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), b.aidx.as<int>());
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,

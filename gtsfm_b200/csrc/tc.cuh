@@ -70,13 +70,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // ---- UMMA -------------------------------------------------------------------------------------------------------
 constexpr uint32_t SBO_BYTES = 128;
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes) {
+// K-major: lbo = byte step between 8-element K chunks, sbo = byte step between 8-row groups.
+// MN-major (operand stored [k][mn] with mn contiguous): lbo = byte step between 8-row K groups, sbo = byte step between
+// 8-element MN chunks (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>, SWIZZLE_NONE branch).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = SBO_BYTES) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);               // start address, bits [0,14)
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading (K-direction) byte offset, bits [16,30)
-  d |= (uint64_t)((SBO_BYTES >> 4) & 0x3FFF) << 32;     // stride (row-group) byte offset, bits [32,46)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version 1 (Blackwell)
   return d;                                             // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;
+
+// ---- cp.async (LDGSTS) 16-byte copies; src_bytes = 0 zero-fills ---------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // kind::f16, A/B = fp16 K-major, D = fp32
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
@@ -110,6 +124,20 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   for (int i = 0; i < 8; ++i) split_h(x[i], h[i], l[i]);
   hi = *reinterpret_cast<uint4*>(h);
   lo = *reinterpret_cast<uint4*>(l);
+}
+// 2^x on the SFU (ex2.approx: max relative error 2^-22, the same order as the operand split); ex2(-inf) = 0
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two floats -> packed (hi, hi) and (lo, lo) half2 words
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // canonical-layout byte offset of (row r, k-chunk c) in a tile of `rows` rows
 __device__ __forceinline__ uint32_t canon_off(int r, int c, int rows) {
