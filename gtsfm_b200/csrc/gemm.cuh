@@ -21,6 +21,7 @@ struct GemmArgs {
   int ldr;
   float scale;  // applied to (acc + bias)
   int head_major;  // 1: write C as [N/64][M][64] (attention head layout) instead of row-major
+  int relu;        // max(., 0) after bias / scale, before the residual
 };
 
 constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
@@ -78,6 +79,7 @@ static __global__ void __launch_bounds__(256) k_gemm_nt(GemmArgs g) {
       float v = acc[i][j];
       if (g.bias) v += g.bias[n];
       v *= g.scale;
+      if (g.relu) v = fmaxf(v, 0.f);
       if (g.resid) v += g.resid[(size_t)m * g.ldr + n];
       if (g.head_major)
         g.C[((size_t)(n >> 6) * g.M + m) * 64 + (n & 63)] = v;
@@ -100,7 +102,7 @@ static inline GemmArgs gemm_linear(const float* x, int ldx, int K, const float* 
   GemmArgs g{};
   g.A1 = x, g.lda1 = ldx, g.K1 = K, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0;
   g.B = w, g.ldb = K, g.C = y, g.ldc = ldy, g.M = M, g.N = N;
-  g.bias = b, g.resid = nullptr, g.ldr = 0, g.scale = 1.f, g.head_major = 0;
+  g.bias = b, g.resid = nullptr, g.ldr = 0, g.scale = 1.f, g.head_major = 0, g.relu = 0;
   return g;
 }
 

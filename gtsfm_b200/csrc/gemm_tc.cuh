@@ -39,6 +39,7 @@ struct GemmTcArgs {
   int ldc;
   int ldch;        // row-major leading dimension of Ch / Cl (ignored when head_major)
   int head_major;  // 1: Ch / Cl (and C) are written as [N/64][M][64] (attention head layout)
+  int relu;        // max(., 0) after bias / scale, before the residual
   int* err_flag;   // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
 };
 
@@ -171,7 +172,9 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
     for (int r = 0; r < 32; ++r) {
       const int m = m0 + warp * 32 + r;
       if (m >= M || n >= g.N) continue;
-      float v = (scratch[r * 33 + lane] + bn) * g.scale + rv[r];
+      float v = (scratch[r * 33 + lane] + bn) * g.scale;
+      if (g.relu) v = fmaxf(v, 0.f);
+      v += rv[r];
       const size_t oh = ((size_t)(n >> 6) * M + m) * 64 + (n & 63);
       if (pb.C) pb.C[g.head_major ? oh : (size_t)m * g.ldc + n] = v;
       if (pb.Ch) {

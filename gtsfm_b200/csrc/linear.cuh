@@ -1,0 +1,127 @@
+// Shared host-side dispatch for the matcher networks: one "linear" / attention call site expressed for both execution
+// paths (tcgen05 split-fp16 planes, or the exact-fp32 SIMT kernels when B2_FORCE_SIMT=1).
+#pragma once
+#include "attn_tc.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gemm_tc.cuh"
+
+struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (same element offsets in all three)
+  const float* f;
+  const __half* h;
+  const __half* l;
+  int* err;     // device flag raised by a timed-out mbarrier wait
+  bool use_tc;
+};
+
+struct Pl {  // split-fp16 planes of an activation
+  __half* hi;
+  __half* lo;
+};
+static inline Pl planes_of(const DevBuf& b, size_t elems) { return {b.as<__half>(), b.as<__half>() + elems}; }
+
+// One linear / GEMM call site, expressed for both execution paths: fp32 views feed the exact-fp32 SIMT kernel,
+// split-fp16 plane views feed the tcgen05 kernel.
+struct LinArgs {
+  const float* a1f = nullptr;
+  Pl a1p{nullptr, nullptr};
+  int lda1 = 0, K1 = 0;
+  const float* a2f = nullptr;
+  Pl a2p{nullptr, nullptr};
+  int lda2 = 0, K2 = 0;
+  const float* w = nullptr;   // weight inside the blob (B operand), or
+  const float* bf = nullptr;  // an fp32 activation B operand with
+  Pl bp{nullptr, nullptr};    // its planes
+  int ldb = 0;
+  const float* bias = nullptr;
+  float scale = 1.f;
+  const float* resid = nullptr;
+  int ldr = 0;
+  float* cf = nullptr;  // fp32 output (always written on the SIMT path; on the tcgen05 path only if tc_want_f32)
+  int ldc = 0;
+  Pl cp{nullptr, nullptr};  // plane output (tcgen05 path)
+  int ldch = 0;
+  int head_major = 0;
+  bool tc_want_f32 = false;
+  int relu = 0;  // max(., 0) after bias / scale, before the residual
+  int M = 0, N = 0;
+};
+
+// `b` (optional) is the same linear applied to the other image of the pair: same weights, shapes and epilogue, so the
+// tcgen05 path runs both as one launch (blockIdx.z).
+static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, const LinArgs& a, const LinArgs* b = nullptr) {
+  if (!tw.use_tc) {
+    const LinArgs* both[2] = {&a, b};
+    for (int i = 0; i < 2; ++i) {
+      if (!both[i] || both[i]->M <= 0 || both[i]->N <= 0) continue;
+      const LinArgs& x = *both[i];
+      GemmArgs g{};
+      g.A1 = x.a1f, g.lda1 = x.lda1, g.K1 = x.K1, g.A2 = x.a2f, g.lda2 = x.lda2, g.K2 = x.K2;
+      g.B = x.w ? x.w : x.bf, g.ldb = x.ldb, g.C = x.cf, g.ldc = x.ldc, g.M = x.M, g.N = x.N;
+      g.bias = x.bias, g.resid = x.resid, g.ldr = x.ldr, g.scale = x.scale, g.head_major = x.head_major, g.relu = x.relu;
+      int rc = launch_gemm(ctx, st, g);
+      if (rc) return rc;
+    }
+    return B2_OK;
+  }
+  if (a.N <= 0 || (a.M <= 0 && (!b || b->M <= 0))) return B2_OK;
+  GemmTcArgs t{};
+  const LinArgs* both[2] = {&a, b};
+  int maxM = 0;
+  double work = 0.0;
+  for (int i = 0; i < 2; ++i) {
+    if (!both[i]) continue;
+    const LinArgs& x = *both[i];
+    GemmTcProblem& q = t.p[i];
+    q.A1h = x.a1p.hi, q.A1l = x.a1p.lo, q.A2h = x.a2p.hi, q.A2l = x.a2p.lo, q.resid = x.resid;
+    q.C = x.tc_want_f32 ? x.cf : nullptr, q.Ch = x.cp.hi, q.Cl = x.cp.lo, q.M = x.M;
+    maxM = x.M > maxM ? x.M : maxM;
+    work += 2.0 * x.M * x.N * (x.K1 + x.K2);
+  }
+  t.lda1 = a.lda1, t.K1 = a.K1, t.lda2 = a.lda2, t.K2 = a.K2;
+  if (a.w) {
+    const size_t off = (size_t)(a.w - tw.f);
+    t.Bh = tw.h + off, t.Bl = tw.l + off;
+  } else {
+    t.Bh = a.bp.hi, t.Bl = a.bp.lo;
+  }
+  t.ldb = a.ldb, t.N = a.N, t.bias = a.bias, t.ldr = a.ldr, t.scale = a.scale, t.ldc = a.ldc, t.ldch = a.ldch;
+  t.head_major = a.head_major, t.relu = a.relu, t.err_flag = tw.err;
+  dim3 grid(cdiv(a.N, TC_N), cdiv(maxM, TC_M), b ? 2 : 1);
+  b2_prof_work(ctx, "k_gemm_tc", work);
+  B2_LAUNCH(ctx, k_gemm_tc, grid, 128, TC_GEMM_SMEM, st, t);
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+
+// One launch, two attention problems.  tcgen05 path: q / k / v / o buffers hold split fp16 planes (hi, then lo at + N * 256).
+struct FlashJob {
+  const DevBuf *q, *k, *v, *o;
+  int nq, nk;
+  int capq, capk;  // allocated rows of the query-side / key-side buffers (lo plane offset = cap * 256 halves)
+};
+static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, const FlashJob& a, const FlashJob& b, float scale) {
+  if (!tw.use_tc) {
+    int rc;
+    if ((rc = launch_flash(ctx, st, a.q->as<float>(), a.k->as<float>(), a.v->as<float>(), a.o->as<float>(), a.nq, a.nk, scale))) return rc;
+    return launch_flash(ctx, st, b.q->as<float>(), b.k->as<float>(), b.v->as<float>(), b.o->as<float>(), b.nq, b.nk, scale);
+  }
+  AttnArgs args{};
+  const FlashJob* jobs[2] = {&a, &b};
+  for (int i = 0; i < 2; ++i) {
+    const FlashJob& j = *jobs[i];
+    AttnProblem& p = args.p[i];
+    const Pl q = planes_of(*j.q, (size_t)j.capq * 256), k = planes_of(*j.k, (size_t)j.capk * 256), v = planes_of(*j.v, (size_t)j.capk * 256),
+             o = planes_of(*j.o, (size_t)j.capq * 256);
+    p.Qh = q.hi, p.Ql = q.lo, p.Kh = k.hi, p.Kl = k.lo, p.Vh = v.hi, p.Vl = v.lo, p.Oh = o.hi, p.Ol = o.lo;
+    p.Nq = j.nq, p.Nk = j.nk;
+  }
+  args.scale = scale, args.err_flag = tw.err;
+  const int qt = cdiv(a.nq > b.nq ? a.nq : b.nq, AT_Q);
+  if (qt <= 0) return B2_OK;
+  b2_prof_work(ctx, "k_flash_tc", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));  // 4 heads x (QK^T + PV) x 2 FLOP/MAC
+  B2_LAUNCH(ctx, k_flash_tc, dim3(qt, 4, 2), 128, AT_SMEM, st, args);
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+

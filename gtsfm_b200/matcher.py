@@ -96,3 +96,75 @@ class B200LightGlueMatcher(MatcherBase):
         eng = self._ensure_engine()
         return eng.match(keypoints_i1.coordinates, descriptors_i1, keypoints_i2.coordinates, descriptors_i2,
                          prune_min_kpts=-1 if self._cpu_semantics else 1536)
+
+
+SUPERGLUE_DESC_DIM = 256
+DEFAULT_NUM_SINKHORN_ITERATIONS = 20  # superglue_matcher.py:27
+SUPERGLUE_MATCH_THRESHOLD = 0.2  # thirdparty/.../superglue.py:201
+
+
+class SuperGlueEngine:
+    def __init__(self, state_dict, device: int = 0, ctx: Optional[_lib.Context] = None):
+        self.ctx = ctx or _lib.Context(device)
+        blob = weights.pack_superglue(weights.load_state_dict(state_dict))
+        self.ctx.check(self.ctx.lib.b2_superglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superglue_set_weights")
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def match(self, kp0, sc0, desc0, kp1, sc1, desc1, shape0, shape1, sinkhorn_iters=DEFAULT_NUM_SINKHORN_ITERATIONS,
+              match_threshold=SUPERGLUE_MATCH_THRESHOLD, return_scores=False):
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (kp0, sc0, desc0, kp1, sc1, desc1)]
+        n0, n1 = len(arrs[0]), len(arrs[3])
+        cap = max(1, min(n0, n1))
+        out = np.empty((cap, 2), np.uint32)
+        sc = np.empty(cap, np.float32)
+        k = _lib.C.c_int(0)
+        rc = self.ctx.lib.b2_superglue_match_host(self.ctx.handle, _lib.ptr(arrs[0]), _lib.ptr(arrs[1]), _lib.ptr(arrs[2]), n0, int(shape0[0]),
+                                                  int(shape0[1]), _lib.ptr(arrs[3]), _lib.ptr(arrs[4]), _lib.ptr(arrs[5]), n1, int(shape1[0]),
+                                                  int(shape1[1]), int(sinkhorn_iters), float(match_threshold), _lib.ptr(out), _lib.ptr(sc),
+                                                  _lib.C.byref(k))
+        self.ctx.check(rc, "superglue_match")
+        self.h2d_bytes += sum(a.nbytes for a in arrs)
+        self.d2h_bytes += k.value * 12 + 4
+        if return_scores:
+            return out[: k.value].copy(), sc[: k.value].copy()
+        return out[: k.value].copy()
+
+
+class B200SuperGlueMatcher(MatcherBase):
+    """SuperGlue on hand-written sm_100a kernels behind GTSfM's MatcherBase (gtsfm/frontend/matcher/superglue_matcher.py:30-115)."""
+
+    def __init__(self, use_cuda: bool = True, use_outdoor_model: bool = True, weights_path: Union[Path, str, dict, None] = None, device: int = 0):
+        super().__init__()
+        if weights_path is None:
+            raise FileNotFoundError("SuperGlue weights_path is required (a superglue_outdoor.pth-style checkpoint)")
+        if not isinstance(weights_path, dict) and not Path(weights_path).exists():
+            raise FileNotFoundError(f"SuperGlue weights not found at {weights_path}")
+        self._use_cuda = use_cuda
+        self._config = {"descriptor_dim": SUPERGLUE_DESC_DIM, "weights": "outdoor" if use_outdoor_model else "indoor",
+                        "sinkhorn_iterations": DEFAULT_NUM_SINKHORN_ITERATIONS}
+        self._weights = weights_path
+        self._device = device
+        self._engine: Optional[SuperGlueEngine] = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        return st
+
+    def _ensure_engine(self) -> SuperGlueEngine:
+        if self._engine is None:
+            self._engine = SuperGlueEngine(self._weights, self._device)
+        return self._engine
+
+    def match(self, keypoints_i1: Keypoints, keypoints_i2: Keypoints, descriptors_i1: np.ndarray, descriptors_i2: np.ndarray,
+              im_shape_i1: Tuple[int, int, int], im_shape_i2: Tuple[int, int, int]) -> np.ndarray:
+        if keypoints_i1.responses is None or keypoints_i2.responses is None:
+            raise ValueError("Responses for keypoints required for SuperGlue")  # superglue_matcher.py:78-79
+        if len(keypoints_i1) == 0 or len(keypoints_i2) == 0:
+            return np.zeros((0, 2), np.uint32)
+        if descriptors_i1.shape[1] != SUPERGLUE_DESC_DIM or descriptors_i2.shape[1] != SUPERGLUE_DESC_DIM:
+            raise Exception("Superglue pretrained network only works on 256 dimensional descriptors")  # :81-82
+        eng = self._ensure_engine()
+        return eng.match(keypoints_i1.coordinates, keypoints_i1.responses, descriptors_i1, keypoints_i2.coordinates,
+                         keypoints_i2.responses, descriptors_i2, im_shape_i1, im_shape_i2, self._config["sinkhorn_iterations"])

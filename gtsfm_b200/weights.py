@@ -113,5 +113,21 @@ def fold_superglue_batchnorm(sd: StateDict, eps: float = 1e-5) -> StateDict:
     return out
 
 
+def superglue_head_major(sd: StateDict) -> StateDict:
+    """Re-index the attention channels from the reference's `channel = dim * 4 + head` interleave
+    (`view(b, 64, 4, n)`, superglue.py:104) to head-major `head * 64 + dim`: rows of the q / k / v projections (and their
+    biases), columns of the merge convolution.  Pure permutation: results are unchanged."""
+    out = dict(sd)
+    perm = np.array([4 * d + h for h in range(4) for d in range(64)])  # new index h*64+d  <- old index 4d+h
+    for l in range(SUPERGLUE_GNN_LAYERS):
+        for j in range(3):
+            k = f"gnn.layers.{l}.attn.proj.{j}"
+            out[k + ".weight"] = np.ascontiguousarray(np.asarray(sd[k + ".weight"])[perm])
+            out[k + ".bias"] = np.ascontiguousarray(np.asarray(sd[k + ".bias"])[perm])
+        k = f"gnn.layers.{l}.attn.merge.weight"
+        out[k] = np.ascontiguousarray(np.asarray(sd[k])[:, perm])
+    return out
+
+
 def pack_superglue(sd: StateDict) -> np.ndarray:
-    return _pack(fold_superglue_batchnorm(sd), SUPERGLUE_ORDER)
+    return _pack(superglue_head_major(fold_superglue_batchnorm(sd)), SUPERGLUE_ORDER)
