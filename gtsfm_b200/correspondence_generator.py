@@ -1,0 +1,67 @@
+"""Batched, device-resident correspondence generator: the L2 seam of SURVEY.md §8b.
+
+Implements `CorrespondenceGeneratorBase.generate_correspondences(client, images, visibility_graph)`
+(gtsfm/frontend/correspondence_generator/correspondence_generator_base.py:19-36) without creating one Dask task per
+image and per pair (det_desc_correspondence_generator.py:65-85): each image is detected once on the GPU, its features stay
+in HBM, every pair of this process's shard is matched there, and only `(K, 2)` index arrays and keypoints come back.
+Under `torch.distributed` (one process per GPU) the pair list is sharded `p mod world` and merged at the end."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import distributed as D
+from .gtsfm_api import HAVE_GTSFM, Keypoints
+from .pipeline import DeviceFeatures, DeviceFrontEnd
+
+if HAVE_GTSFM:  # pragma: no cover
+    from gtsfm.frontend.correspondence_generator.correspondence_generator_base import CorrespondenceGeneratorBase as _Base
+else:
+    _Base = object
+
+
+class B200CorrespondenceGenerator(_Base):
+    def __init__(self, superpoint_weights, lightglue_weights, max_keypoints: int = 5000, device: int = 0, cpu_semantics: bool = True):
+        self._sp, self._lg = superpoint_weights, lightglue_weights
+        self._max_keypoints, self._device, self._cpu_semantics = max_keypoints, device, cpu_semantics
+        self._fe: Optional[DeviceFrontEnd] = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_fe"] = None
+        return st
+
+    def _front_end(self) -> DeviceFrontEnd:
+        if self._fe is None:
+            self._fe = DeviceFrontEnd(self._sp, self._lg, device=self._device, max_keypoints=self._max_keypoints,
+                                      cpu_semantics=self._cpu_semantics)
+        return self._fe
+
+    def generate_correspondences(self, client, images: Sequence, visibility_graph: Sequence[Tuple[int, int]]):
+        """-> (List[Keypoints] per image, Dict[(i1, i2), (K, 2) int64 match rows])."""
+        fe = self._front_end()
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        mine = D.shard_pairs(list(visibility_graph), rank, world)
+        feats: Dict[int, DeviceFeatures] = {}
+        for idx in (range(len(images)) if world == 1 else D.images_needed(mine)):
+            img = images[idx].result() if hasattr(images[idx], "result") else images[idx]  # Dask Future or Image
+            arr = img.value_array if hasattr(img, "value_array") else np.asarray(img)
+            feats[idx] = fe.detect(torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device))
+        local: Dict[Tuple[int, int], np.ndarray] = {}
+        for (i1, i2) in mine:
+            m, _ = fe.match(feats[i1], feats[i2])
+            local[(i1, i2)] = m.cpu().numpy()
+        matches = D.gather_pair_results(local)
+        keypoints: List[Optional[Keypoints]] = [None] * len(images)
+        for idx, f in feats.items():
+            keypoints[idx] = Keypoints(f.kp.cpu().numpy(), scales=None, responses=f.score.cpu().numpy())
+        if world > 1:  # every rank returns the keypoints of all images, like the reference's gather (:83-85)
+            parts: List[Dict[int, Keypoints]] = [None] * world  # type: ignore[list-item]
+            torch.distributed.all_gather_object(parts, {i: k for i, k in enumerate(keypoints) if k is not None})
+            for part in parts:
+                for i, k in part.items():
+                    keypoints[i] = keypoints[i] or k
+        return keypoints, matches

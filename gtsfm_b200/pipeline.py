@@ -107,6 +107,4 @@ class DeviceFrontEnd:
         return E.reshape(3, 3), R.reshape(3, 3), t, n.value, mask[:k]
 
 
-def shard_pairs(pairs: List[Tuple[int, int]], rank: int, world: int) -> List[Tuple[int, int]]:
-    """Pair p (in visibility-graph order) -> GPU p mod world: no data-path collective."""
-    return [p for i, p in enumerate(pairs) if i % world == rank]
+from .distributed import shard_pairs  # noqa: E402,F401  (re-export: `p mod world` partitioner)

@@ -1,0 +1,51 @@
+"""GPU: the device-resident batched path (DeviceFrontEnd / B200CorrespondenceGenerator) agrees with the per-call plugins."""
+import numpy as np
+import pytest
+import torch
+
+from gtsfm_b200 import synthetic as syn
+from gtsfm_b200.correspondence_generator import B200CorrespondenceGenerator
+from gtsfm_b200.detector_descriptor import SuperPointEngine
+from gtsfm_b200.gtsfm_api import Image
+from gtsfm_b200.matcher import LightGlueEngine
+from gtsfm_b200.pipeline import DeviceFrontEnd
+from oracle import verifier_ref as vr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_path_equals_host_path(b200_ctx):
+    sp_sd, lg_sd = syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "sharp")
+    frames, cal = syn.synthetic_sequence(3, 240, 320)
+    fe = DeviceFrontEnd(sp_sd, lg_sd, max_keypoints=600, ctx=b200_ctx)
+    fa = fe.detect(torch.from_numpy(frames[0]).cuda())
+    fb = fe.detect(torch.from_numpy(frames[2]).cuda())
+    sp = SuperPointEngine(sp_sd, ctx=b200_ctx)
+    xy, sc = sp.detect(frames[0])
+    # device top-k = the 600 largest scores, kept in row-major order
+    order = np.argsort(-sc, kind="stable")[:600]
+    assert len(fa) == 600 and np.array_equal(fa.kp.cpu().numpy(), xy[np.sort(order)])
+    np.testing.assert_allclose(fa.desc.cpu().numpy(), sp.describe(fa.kp.cpu().numpy()), atol=1e-6)
+    m, stop = fe.match(fa, fb)
+    lg = LightGlueEngine(lg_sd, ctx=b200_ctx)
+    mh = lg.match(fa.kp.cpu().numpy(), fa.desc.cpu().numpy(), fb.kp.cpu().numpy(), fb.desc.cpu().numpy())
+    assert np.array_equal(m.cpu().numpy(), mh) and len(mh) > 50
+    E, R, t, ninl, mask = fe.verify(fa, fb, m, cal, cal, 4.0)
+    assert E is not None and ninl > 0.8 * len(mh) and int(mask.sum().item()) == ninl
+    n1 = vr.calibrate(fa.kp.cpu().numpy()[mh[:, 0]], *cal)
+    n2 = vr.calibrate(fb.kp.cpu().numpy()[mh[:, 1]], *cal)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), vr.sampson_sq(E, n1, n2) < (4.0 / cal[0]) ** 2)
+    assert abs(np.linalg.det(R) - 1) < 1e-6 and abs(np.linalg.norm(t) - 1) < 1e-6
+
+
+def test_correspondence_generator_contract():
+    sp_sd, lg_sd = syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "sharp")
+    frames, _ = syn.synthetic_sequence(4, 240, 320)
+    gen = B200CorrespondenceGenerator(sp_sd, lg_sd, max_keypoints=500)
+    graph = [(0, 1), (0, 2), (1, 3)]
+    kps, matches = gen.generate_correspondences(None, [Image(f) for f in frames], graph)
+    assert len(kps) == 4 and all(len(k) <= 500 and k.responses is not None for k in kps)
+    assert sorted(matches) == sorted(graph)
+    for (i1, i2), m in matches.items():
+        assert m.dtype == np.int64 and m.shape[1] == 2 and len(m) > 20
+        assert m[:, 0].max() < len(kps[i1]) and m[:, 1].max() < len(kps[i2])
