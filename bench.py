@@ -37,7 +37,7 @@ LOOKAHEAD = 20
 NEW_FRAMES = 2
 PAIRS_PER_STEP = LOOKAHEAD * NEW_FRAMES
 THR_PX = 4.0
-DOMINANT_KERNEL = "k_flash_attn"
+DOMINANT_KERNEL = "k_flash"  # prefix: k_flash_tc (tcgen05) or k_flash_attn (forced SIMT)
 CONFIG = {
     "workload": "SuperPoint+LightGlue+RANSAC-5pt, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] steady state, deep_front_end.yaml matcher)",
     "frame": [H, W], "max_keypoints": MAX_KP, "lookahead": LOOKAHEAD, "new_frames_per_step": NEW_FRAMES,

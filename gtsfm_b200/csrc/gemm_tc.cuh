@@ -41,6 +41,7 @@ struct GemmTcArgs {
   int head_major;  // 1: Ch / Cl (and C) are written as [N/64][M][64] (attention head layout)
   int relu;        // max(., 0) after bias / scale, before the residual
   int* err_flag;   // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
+  long long* timing;  // debug: clock64 stamps of CTA (0,0,0) (null in production)
 };
 
 constexpr int TC_M = 128, TC_N = 64, TC_K = 64, TC_STAGES = 2;
@@ -55,15 +56,13 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + TC_STAGES);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool stamp = g.timing && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int ts = 0;
+  if (stamp) g.timing[ts++] = clock64();
   const GemmTcProblem& pb = g.p[blockIdx.z];
   const int M = pb.M;
   const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * TC_N;
   if (m0 >= M) return;  // uniform; before any allocation / barrier
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 2 * TC_N);
-  if (t == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) tc::mbar_init(&bar[s], 1);
-    tc::fence_mbar_init();
-  }
   const uint32_t smem0 = tc::smem_u32(tsm);
   const int K = g.K1 + g.K2, nk = K / TC_K;
 
@@ -103,12 +102,18 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
     }
   };
 
-  load_chunk(0, 0);
+  load_chunk(0, 0);  // in flight while TMEM is being allocated
   tc::cp_async_commit();
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 2 * TC_N);
+  if (t == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) tc::mbar_init(&bar[s], 1);
+    tc::fence_mbar_init();
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  if (stamp) g.timing[ts++] = clock64();  // after alloc + first loads issued + sync
   const uint32_t idesc = tc::idesc_f16(TC_M, TC_N);
   const uint32_t lboA = (TC_M / 8) * 128, lboB = (TC_N / 8) * 128;
   bool ok = true;
@@ -122,33 +127,44 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
     }
     tc::cp_async_commit();
     tc::cp_async_wait<1>();  // chunk kc has landed (only the newest group may still be in flight)
+    if (stamp) g.timing[ts++] = clock64();  // data landed
     tc::fence_proxy_async();
     __syncthreads();
+    if (stamp) g.timing[ts++] = clock64();  // after fence + sync
     if (t == 0) {
       tc::fence_after_sync();
       const uint32_t aH = smem0 + stage * TC_STAGE_BYTES, aL = aH + TC_A_BYTES, bH = aH + 2 * TC_A_BYTES, bL = bH + TC_B_BYTES;
+      const uint64_t bAh = tc::smem_desc(aH, lboA), bAl = tc::smem_desc(aL, lboA), bBh = tc::smem_desc(bH, lboB), bBl = tc::smem_desc(bL, lboB);
 #pragma unroll
       for (int s = 0; s < TC_K / 16; ++s) {
-        const uint64_t dAh = tc::smem_desc(aH + 2 * s * lboA, lboA), dAl = tc::smem_desc(aL + 2 * s * lboA, lboA);
-        const uint64_t dBh = tc::smem_desc(bH + 2 * s * lboB, lboB), dBl = tc::smem_desc(bL + 2 * s * lboB, lboB);
+        // advancing the 14-bit start-address field (units of 16 B) by one K step; the tiles never cross its range
+        const uint64_t dAh = bAh + ((2 * s * lboA) >> 4), dAl = bAl + ((2 * s * lboA) >> 4);
+        const uint64_t dBh = bBh + ((2 * s * lboB) >> 4), dBl = bBl + ((2 * s * lboB) >> 4);
         const uint32_t first = (kc == 0 && s == 0) ? 0u : 1u;
         tc::umma_f16(tmem, dAh, dBh, idesc, first);         // acc0 (+)= Ah Bh
         tc::umma_f16(tmem + TC_N, dAh, dBl, idesc, first);  // acc1 (+)= Ah Bl
         tc::umma_f16(tmem + TC_N, dAl, dBh, idesc, 1u);     // acc1  += Al Bh
       }
       tc::umma_commit(&bar[stage]);
+      if (stamp) g.timing[ts++] = clock64();  // MMAs issued
     }
   }
   // all MMAs complete when the last chunk's commit arrives (commits are ordered)
   ok = tc::mbar_wait(&bar[(nk - 1) & 1], ((nk - 1) >> 1) & 1) && ok;
+  if (stamp) g.timing[ts++] = clock64();  // last MMA complete
   tc::cp_async_wait<0>();
   tc::fence_after_sync();
   if (!ok && g.err_flag) *g.err_flag = 1;
   __syncthreads();  // every warp is past its waits before the operand tiles are reused as scratch
 
   // ---- epilogue ---------------------------------------------------------------------------------------------------
+  // Per warp: 32 accumulator rows.  All row-invariant address arithmetic is hoisted; the row loop only strides pointers.
   float* scratch = reinterpret_cast<float*>(tsm) + warp * (32 * 33);
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const int mw = m0 + warp * 32;                   // first row of this warp
+  const int rows = min(32, M - mw);                // warp-uniform; may be <= 0 for the ragged last tile
+  const float scale = g.scale;
+  const int relu = g.relu;
 #pragma unroll 1
   for (int cc = 0; cc < TC_N / 32; ++cc) {
     if (n0 + cc * 32 >= g.N) break;  // uniform
@@ -161,35 +177,59 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
     }
     __syncwarp();
     const int n = n0 + cc * 32 + lane;
-    const float bn = (g.bias && n < g.N) ? g.bias[n] : 0.f;
-    float rv[32];  // residual rows fetched up front: 32 independent coalesced loads in flight instead of a serial chain
+    if (n < g.N && rows > 0) {
+      const float bn = g.bias ? g.bias[n] : 0.f;
+      // element offset of (row mw, column n) and the per-row stride, for the row-major and the head-major layouts
+      const size_t off_h = ((size_t)(n >> 6) * M + mw) * 64 + (n & 63);
+      const size_t off_c = g.head_major ? off_h : (size_t)mw * g.ldc + n;
+      const size_t off_s = g.head_major ? off_h : (size_t)mw * g.ldch + n;
+      const int str_c = g.head_major ? 64 : g.ldc, str_s = g.head_major ? 64 : g.ldch;
+      const float* rp = pb.resid ? pb.resid + (size_t)mw * g.ldr + n : nullptr;
+      float* cp = pb.C ? pb.C + off_c : nullptr;
+      __half* hp = pb.Ch ? pb.Ch + off_s : nullptr;
+      __half* lp = pb.Ch ? pb.Cl + off_s : nullptr;
+      const float* sp = scratch + lane;
+      if (rp) {
+        float rv[32];  // residual rows fetched up front: independent coalesced loads in flight, not a serial chain
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const int m = m0 + warp * 32 + r;
-      rv[r] = (pb.resid && m < M && n < g.N) ? pb.resid[(size_t)m * g.ldr + n] : 0.f;
-    }
+        for (int r = 0; r < 32; ++r) rv[r] = r < rows ? rp[(size_t)r * g.ldr] : 0.f;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const int m = m0 + warp * 32 + r;
-      if (m >= M || n >= g.N) continue;
-      float v = (scratch[r * 33 + lane] + bn) * g.scale;
-      if (g.relu) v = fmaxf(v, 0.f);
-      v += rv[r];
-      const size_t oh = ((size_t)(n >> 6) * M + m) * 64 + (n & 63);
-      if (pb.C) pb.C[g.head_major ? oh : (size_t)m * g.ldc + n] = v;
-      if (pb.Ch) {
-        __half hh, ll;
-        tc::split_h(v, hh, ll);
-        const size_t o = g.head_major ? oh : (size_t)m * g.ldch + n;
-        pb.Ch[o] = hh;
-        pb.Cl[o] = ll;
+        for (int r = 0; r < 32; ++r) {
+          if (r < rows) {
+            float v = (sp[r * 33] + bn) * scale;
+            if (relu) v = fmaxf(v, 0.f);
+            v += rv[r];
+            if (cp) cp[(size_t)r * str_c] = v;
+            if (hp) {
+              __half hh, ll;
+              tc::split_h(v, hh, ll);
+              hp[(size_t)r * str_s] = hh;
+              lp[(size_t)r * str_s] = ll;
+            }
+          }
+        }
+      } else {
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r) {
+          float v = (sp[r * 33] + bn) * scale;
+          if (relu) v = fmaxf(v, 0.f);
+          if (cp) cp[(size_t)r * str_c] = v;
+          if (hp) {
+            __half hh, ll;
+            tc::split_h(v, hh, ll);
+            hp[(size_t)r * str_s] = hh;
+            lp[(size_t)r * str_s] = ll;
+          }
+        }
       }
     }
     __syncwarp();
   }
+  if (stamp) g.timing[ts++] = clock64();  // epilogue done
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 2 * TC_N);
+  if (stamp) g.timing[ts++] = clock64(), g.timing[31] = ts;
 }
 
 // fp32 -> fp16 hi / lo * 2^11 planes (weights once at load time; network inputs once per call)

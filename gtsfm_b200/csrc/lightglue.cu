@@ -516,6 +516,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaDeviceSynchronize());
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
   {
     const char* e = getenv("B2_FORCE_SIMT");
@@ -529,7 +530,10 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
 }
 
 static inline TcWeights lg_tw(LightGlueState* s) {
-  return TcWeights{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
+  TcWeights t{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
+  const char* e = getenv("B2_NO_TMA");
+  t.use_tma = !(e && e[0] == '1');
+  return t;
 }
 static int lg_linear(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LinArgs& a, const LinArgs* b = nullptr) {
   return run_linear(ctx, st, lg_tw(s), a, b);

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (same element offsets in all three)
   const float* f;
@@ -12,6 +13,7 @@ struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (s
   const __half* l;
   int* err;     // device flag raised by a timed-out mbarrier wait
   bool use_tc;
+  bool use_tma = true;  // TMA-fed kernel (default) vs the cp.async kernel (B2_NO_TMA=1)
 };
 
 struct Pl {  // split-fp16 planes of an activation
@@ -65,6 +67,43 @@ static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     return B2_OK;
   }
   if (a.N <= 0 || (a.M <= 0 && (!b || b->M <= 0))) return B2_OK;
+  if (tw.use_tma && tma_encoder()) {
+    GemmTmaMaps maps;
+    GemmTmaArgs q{};
+    const LinArgs* both[2] = {&a, b};
+    int maxM = 0;
+    double work = 0.0;
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) {
+      const LinArgs& x = both[i] ? *both[i] : a;  // unused second slot mirrors the first (never launched: grid.z = 1)
+      ok = ok && tma_map_2d(&maps.a1h[i], x.a1p.hi, x.M, x.K1, x.lda1, TM_M) && tma_map_2d(&maps.a1l[i], x.a1p.lo, x.M, x.K1, x.lda1, TM_M);
+      if (x.K2 > 0)
+        ok = ok && tma_map_2d(&maps.a2h[i], x.a2p.hi, x.M, x.K2, x.lda2, TM_M) && tma_map_2d(&maps.a2l[i], x.a2p.lo, x.M, x.K2, x.lda2, TM_M);
+      else
+        maps.a2h[i] = maps.a1h[i], maps.a2l[i] = maps.a1l[i];
+      if (!both[i]) continue;
+      GemmTcProblem& pr = q.p[i];
+      pr.resid = x.resid, pr.C = x.tc_want_f32 ? x.cf : nullptr, pr.Ch = x.cp.hi, pr.Cl = x.cp.lo, pr.M = x.M;
+      maxM = x.M > maxM ? x.M : maxM;
+      work += 2.0 * x.M * x.N * (x.K1 + x.K2);
+    }
+    const __half *bh, *bl;
+    if (a.w) {
+      const size_t off = (size_t)(a.w - tw.f);
+      bh = tw.h + off, bl = tw.l + off;
+    } else {
+      bh = a.bp.hi, bl = a.bp.lo;
+    }
+    ok = ok && tma_map_2d(&maps.bh, bh, a.N, a.K1 + a.K2, a.ldb, TM_N) && tma_map_2d(&maps.bl, bl, a.N, a.K1 + a.K2, a.ldb, TM_N);
+    if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    q.K1 = a.K1, q.K2 = a.K2, q.N = a.N, q.bias = a.bias, q.ldr = a.ldr, q.scale = a.scale, q.ldc = a.ldc, q.ldch = a.ldch;
+    q.head_major = a.head_major, q.relu = a.relu, q.err_flag = tw.err;
+    dim3 grid(cdiv(a.N, TM_N), cdiv(maxM, TM_M), b ? 2 : 1);
+    b2_prof_work(ctx, "k_gemm_tma", work);
+    B2_LAUNCH(ctx, k_gemm_tma, grid, 128, TM_GEMM_SMEM, st, maps, q);
+    B2_CHECK_LAUNCH(ctx);
+    return B2_OK;
+  }
   GemmTcArgs t{};
   const LinArgs* both[2] = {&a, b};
   int maxM = 0;
