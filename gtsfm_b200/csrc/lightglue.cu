@@ -50,7 +50,7 @@ struct LightGlueState {
   ConfW tw[LG_LAYERS - 1];
   float thr[LG_LAYERS];
   LgSide side[2];
-  DevBuf sim, counters, bbox, outm, outs;
+  DevBuf sim, counters, bbox, outm, outs, attn_part[2], attn_ml[2];
   HostBuf hread;
 };
 
@@ -68,6 +68,7 @@ void lg_destroy(b2_context* ctx) {
     for (DevBuf* b : bufs) b->release();
   }
   s->sim.release();
+  for (int i = 0; i < 2; ++i) s->attn_part[i].release(), s->attn_ml[i].release();
   s->counters.release();
   s->bbox.release();
   s->outm.release();
@@ -518,6 +519,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
   {
     const char* e = getenv("B2_FORCE_SIMT");
     s->use_tc = !(e && e[0] == '1');
@@ -533,6 +535,7 @@ static inline TcWeights lg_tw(LightGlueState* s) {
   TcWeights t{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
   const char* e = getenv("B2_NO_TMA");
   t.use_tma = !(e && e[0] == '1');
+  t.attn_part = s->attn_part, t.attn_ml = s->attn_ml;
   return t;
 }
 static int lg_linear(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LinArgs& a, const LinArgs* b = nullptr) {

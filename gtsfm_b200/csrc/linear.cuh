@@ -6,6 +6,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
+#include "attn_ws.cuh"
 
 struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (same element offsets in all three)
   const float* f;
@@ -13,7 +14,10 @@ struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (s
   const __half* l;
   int* err;     // device flag raised by a timed-out mbarrier wait
   bool use_tc;
-  bool use_tma = true;  // TMA-fed kernel (default) vs the cp.async kernel (B2_NO_TMA=1)
+  bool use_tma = true;  // TMA-fed kernels (default) vs the cp.async kernels (B2_NO_TMA=1)
+  DevBuf* attn_part = nullptr;  // [2] scratch for key-split attention partials (O) ...
+  DevBuf* attn_ml = nullptr;    // [2] ... and (m, l)
+  int sm_count = 148;
 };
 
 struct Pl {  // split-fp16 planes of an activation
@@ -145,8 +149,54 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     if ((rc = launch_flash(ctx, st, a.q->as<float>(), a.k->as<float>(), a.v->as<float>(), a.o->as<float>(), a.nq, a.nk, scale))) return rc;
     return launch_flash(ctx, st, b.q->as<float>(), b.k->as<float>(), b.v->as<float>(), b.o->as<float>(), b.nq, b.nk, scale);
   }
-  AttnArgs args{};
   const FlashJob* jobs[2] = {&a, &b};
+  if (tw.use_tma && tma_encoder() && tw.attn_part) {
+    AttnWsMaps maps;
+    AttnWsArgs wa{};
+    const int qt = cdiv(a.nq > b.nq ? a.nq : b.nq, 2 * AW_Q);
+    if (qt <= 0) return B2_OK;
+    // key-range split factor: fewest (rounds of CTAs over the SMs) / split
+    const int items = qt * 4 * 2;
+    int nsplit = 1;
+    double best = 1e30;
+    const int max_tiles = cdiv(a.nk > b.nk ? a.nk : b.nk, AW_KV);
+    for (int sp = 1; sp <= 4 && sp <= max_tiles; ++sp) {
+      const double cost = (double)cdiv(items * sp, tw.sm_count) / sp + 0.03 * (sp - 1);  // small penalty for the merge pass
+      if (cost < best - 1e-9) best = cost, nsplit = sp;
+    }
+    bool okm = true;
+    for (int i = 0; i < 2; ++i) {
+      const FlashJob& j = *jobs[i];
+      const Pl q = planes_of(*j.q, (size_t)j.capq * 256), k = planes_of(*j.k, (size_t)j.capk * 256), v = planes_of(*j.v, (size_t)j.capk * 256),
+               o = planes_of(*j.o, (size_t)j.capq * 256);
+      okm = okm && tma_map_2d(&maps.qh[i], q.hi, (uint64_t)4 * j.nq, 64, 64, AW_Q) && tma_map_2d(&maps.ql[i], q.lo, (uint64_t)4 * j.nq, 64, 64, AW_Q);
+      okm = okm && tma_map_2d(&maps.kh[i], k.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&maps.kl[i], k.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+      okm = okm && tma_map_2d(&maps.vh[i], v.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&maps.vl[i], v.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+      AttnWsProblem& p = wa.p[i];
+      p.Oh = o.hi, p.Ol = o.lo, p.Nq = j.nq, p.Nk = j.nk;
+      if (nsplit > 1) {
+        B2_CUDA(ctx, tw.attn_part[i].ensure((size_t)nsplit * j.nq * 256 * 4));
+        B2_CUDA(ctx, tw.attn_ml[i].ensure((size_t)nsplit * 4 * j.nq * 2 * 4));
+        p.Opart = tw.attn_part[i].as<float>(), p.ml = tw.attn_ml[i].as<float>();
+      }
+    }
+    if (!okm) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (attention)");
+    wa.scale = scale, wa.nsplit = nsplit, wa.err_flag = tw.err;
+    b2_prof_work(ctx, "k_flash_ws", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));
+    B2_LAUNCH(ctx, k_flash_ws, dim3(qt, 4, 2 * nsplit), AW_THREADS, AW_SMEM, st, maps, wa);
+    B2_CHECK_LAUNCH(ctx);
+    if (nsplit > 1) {
+      for (int i = 0; i < 2; ++i) {
+        const FlashJob& j = *jobs[i];
+        const Pl o = planes_of(*j.o, (size_t)j.capq * 256);
+        B2_LAUNCH(ctx, k_attn_merge, cdiv(j.nq * 128, 256), 256, 0, st, tw.attn_part[i].as<float>(), tw.attn_ml[i].as<float>(), j.nq, nsplit,
+                  o.hi, o.lo);
+        B2_CHECK_LAUNCH(ctx);
+      }
+    }
+    return B2_OK;
+  }
+  AttnArgs args{};
   for (int i = 0; i < 2; ++i) {
     const FlashJob& j = *jobs[i];
     AttnProblem& p = args.p[i];

@@ -37,13 +37,13 @@ struct SuperGlueState {
   float *wf = nullptr, *bf = nullptr;
   float bin_score = 0.f;
   SgSide side[2];
-  DevBuf sim, counters;
+  DevBuf sim, counters, attn_part[2], attn_ml[2];
 };
 
 void sg_destroy(b2_context* ctx) {
   if (!ctx->sg) return;
   SuperGlueState* s = ctx->sg;
-  DevBuf* top[] = {&s->wblob, &s->wblob_h, &s->wblob_l, &s->errflag, &s->sim, &s->counters};
+  DevBuf* top[] = {&s->wblob, &s->wblob_h, &s->wblob_l, &s->errflag, &s->sim, &s->counters, &s->attn_part[0], &s->attn_part[1], &s->attn_ml[0], &s->attn_ml[1]};
   for (DevBuf* b : top) b->release();
   for (auto& sd : s->side) {
     DevBuf* bufs[] = {&sd.x, &sd.xs, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.hs, &sd.md, &sd.u, &sd.vv, &sd.best, &sd.arg};
@@ -333,6 +333,7 @@ extern "C" int b2_superglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   const char* e = getenv("B2_FORCE_SIMT");
   s->use_tc = !(e && e[0] == '1');
@@ -347,7 +348,12 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
   if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "superglue weights not set");
   *out_k = 0;
   if (n0 <= 0 || n1 <= 0) return B2_OK;  // superglue.py:233-240
-  const TcWeights tw{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
+  TcWeights tw{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
+  {
+    const char* e = getenv("B2_NO_TMA");
+    tw.use_tma = !(e && e[0] == '1');
+    tw.attn_part = s->attn_part, tw.attn_ml = s->attn_ml, tw.sm_count = ctx->sm_count;
+  }
   int rc;
   const float* kps[2] = {kp0, kp1};
   const float* scs[2] = {sc0, sc1};
