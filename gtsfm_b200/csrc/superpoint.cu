@@ -9,7 +9,10 @@
 // segment, which is what both the implicit-GEMM K loop and the bilinear descriptor gather want); conv weights repacked
 // at load to [tap][cin][cout]; 1x1 weights to [cin][cout]; score / NMS maps (H8, W8) fp32; dense descriptors
 // (Hc, Wc, 256) fp32; keypoints as (x, y) float pairs in torch.nonzero (row-major) order.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "conv_tma.cuh"
 
 namespace {
 
@@ -27,6 +30,10 @@ struct SuperPointState {
   DevBuf wblob;
   float* w[SP_NCONV] = {};
   float* b[SP_NCONV] = {};
+  // tcgen05 path: 3x3 weights as [cout][tap * cin] split-fp16 planes (B operand of the implicit GEMM)
+  DevBuf wsplit_h, wsplit_l, errflag;
+  size_t wsoff[SP_NCONV] = {};
+  bool use_tc = true;
   // workspace
   DevBuf gray, a0, a1, feat, head, heat, nms, rowcnt, rowoff, dense, kpxy, kpsc;
   int H = 0, W = 0, Hc = 0, Wc = 0;
@@ -37,7 +44,7 @@ struct SuperPointState {
 void sp_destroy(b2_context* ctx) {
   if (!ctx->sp) return;
   SuperPointState* s = ctx->sp;
-  DevBuf* bufs[] = {&s->wblob, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
+  DevBuf* bufs[] = {&s->wblob, &s->wsplit_h, &s->wsplit_l, &s->errflag, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
                     &s->rowcnt, &s->rowoff, &s->dense, &s->kpxy, &s->kpsc};
   for (DevBuf* b : bufs) b->release();
   delete s;
@@ -68,7 +75,8 @@ __global__ void k_to_gray(const uint8_t* __restrict__ img, size_t pitch, int cha
 // conv1a: 1 -> 64 channels, 3x3, pad 1, bias, ReLU; input gray u8 / 255 (gtsfm/.../superpoint.py:74).
 // block = 256 threads = 16 pixels x 16 channel groups of 4.
 __global__ void __launch_bounds__(256) k_conv1a(const uint8_t* __restrict__ gray, const float* __restrict__ wt /*[9][64]*/,
-                                                 const float* __restrict__ bias, float* __restrict__ out, int H, int W) {
+                                                 const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                                                 __half* __restrict__ oh, __half* __restrict__ ol) {
   __shared__ float ws[9 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 9 * 64; i += 256) ws[i] = wt[i];
@@ -92,7 +100,15 @@ __global__ void __launch_bounds__(256) k_conv1a(const uint8_t* __restrict__ gray
     }
   }
   float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-  *reinterpret_cast<float4*>(out + (size_t)pix * 64 + cg * 4) = o;
+  if (oh) {  // split fp16 planes for the tcgen05 convolutions
+    uint32_t h01, l01, h23, l23;
+    tc::split2(o.x, o.y, h01, l01);
+    tc::split2(o.z, o.w, h23, l23);
+    *reinterpret_cast<uint2*>(oh + (size_t)pix * 64 + cg * 4) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(ol + (size_t)pix * 64 + cg * 4) = make_uint2(l01, l23);
+  } else {
+    *reinterpret_cast<float4*>(out + (size_t)pix * 64 + cg * 4) = o;
+  }
 }
 
 // Generic 3x3 conv, pad 1, bias + ReLU, optional fused 2x2/2 max-pool, NHWC fp32, SIMT fp32 FMA (exact-fp32 path).
@@ -511,6 +527,31 @@ static int sp_conv3x3(b2_context* ctx, cudaStream_t st, const float* in, int li,
   return B2_OK;
 }
 
+// tcgen05 implicit-GEMM convolution on split-fp16 NHWC planes (conv_tma.cuh).  `in` / `out` buffers hold the hi plane
+// followed by the lo plane (+ pixels * channels halves).
+static int sp_conv3x3_tc(b2_context* ctx, cudaStream_t st, const DevBuf& in, int li, int H, int W, bool pool, DevBuf* out_planes,
+                         float* out_f32) {
+  SuperPointState* s = ctx->sp;
+  const int Cin = SP_CI[li], Cout = SP_CO[li];
+  const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
+  ConvTmaMaps maps;
+  const __half* ih = in.as<__half>();
+  const __half* il = ih + (size_t)H * W * Cin;
+  const __half* wh = s->wsplit_h.as<__half>() + s->wsoff[li];
+  const __half* wl = s->wsplit_l.as<__half>() + s->wsoff[li];
+  bool ok = tma_map_nhwc(&maps.ah, ih, H, W, Cin) && tma_map_nhwc(&maps.al, il, H, W, Cin) &&
+            tma_map_2d(&maps.wh, wh, Cout, 9 * Cin, 9 * Cin, CV_N) && tma_map_2d(&maps.wl, wl, Cout, 9 * Cin, 9 * Cin, CV_N);
+  if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (conv)");
+  ConvTmaArgs a{};
+  a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.pool = pool ? 1 : 0, a.bias = s->b[li];
+  if (out_planes) a.Oh = out_planes->as<__half>(), a.Ol = a.Oh + (size_t)OH * OW * Cout;
+  a.Of = out_f32, a.err_flag = s->errflag.as<int>();
+  b2_prof_work(ctx, "k_conv_tma", 2.0 * 9.0 * H * W * Cin * Cout);
+  B2_LAUNCH(ctx, k_conv_tma, dim3(cdiv(W, CV_TW), cdiv(H, CV_TH), Cout / CV_N), 128, CV_SMEM, st, maps, a);
+  B2_CHECK_LAUNCH(ctx);
+  return B2_OK;
+}
+
 static size_t nms_smem_bytes() { return (size_t)NREG * 4 * sizeof(float) + (size_t)NREG * 3; }
 
 extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, size_t n_floats) {
@@ -558,6 +599,42 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
     B2_CUDA(ctx, cudaMemcpy(s->w[l], packed.data() + woff[l], nw * sizeof(float), cudaMemcpyHostToDevice));
     B2_CUDA(ctx, cudaMemcpy(s->b[l], packed.data() + boff[l], SP_CO[l] * sizeof(float), cudaMemcpyHostToDevice));
   }
+  // tcgen05 path: [cout][tap * cin + ci] fp32 -> split planes (one device split kernel over a host-built fp32 staging copy)
+  {
+    size_t tot = 0;
+    for (int l = 0; l < SP_NCONV; ++l) {
+      s->wsoff[l] = tot;
+      if (SP_K[l] == 3 && SP_CI[l] >= 64) tot += (size_t)SP_CO[l] * 9 * SP_CI[l];
+    }
+    std::vector<float> stage(tot);
+    size_t src2 = 0;
+    for (int l = 0; l < SP_NCONV; ++l) {
+      const int co = SP_CO[l], ci = SP_CI[l], kk = SP_K[l] * SP_K[l];
+      if (SP_K[l] == 3 && ci >= 64) {
+        const float* w = blob + src2;  // OIHW
+        float* d = stage.data() + s->wsoff[l];
+        for (int o = 0; o < co; ++o)
+          for (int tp = 0; tp < 9; ++tp)
+            for (int i = 0; i < ci; ++i) d[(size_t)o * 9 * ci + tp * ci + i] = w[((size_t)o * ci + i) * 9 + tp];
+      }
+      src2 += (size_t)co * ci * kk + co;
+    }
+    DevBuf tmp;
+    B2_CUDA(ctx, tmp.ensure(tot * sizeof(float)));
+    B2_CUDA(ctx, s->wsplit_h.ensure(tot * sizeof(__half)));
+    B2_CUDA(ctx, s->wsplit_l.ensure(tot * sizeof(__half)));
+    B2_CUDA(ctx, s->errflag.ensure(16));
+    B2_CUDA(ctx, cudaMemset(s->errflag.p, 0, 16));
+    B2_CUDA(ctx, cudaMemcpy(tmp.p, stage.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    B2_LAUNCH(ctx, k_split_f32, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)0, tmp.as<float>(), tot, s->wsplit_h.as<__half>(),
+              s->wsplit_l.as<__half>());
+    B2_CHECK_LAUNCH(ctx);
+    B2_CUDA(ctx, cudaDeviceSynchronize());
+    tmp.release();
+    B2_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
+    const char* e = getenv("B2_FORCE_SIMT");
+    s->use_tc = !(e && e[0] == '1') && tma_encoder() != nullptr;
+  }
   B2_CUDA(ctx, cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
   s->loaded = true;
   return B2_OK;
@@ -593,9 +670,27 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
 
   B2_LAUNCH(ctx, k_to_gray, dim3(cdiv(W, 256), H), 256, 0, st, image, pitch, channels, H, W, s->gray.as<uint8_t>());
   B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W);
-  B2_CHECK_LAUNCH(ctx);
   int rc;
+  const bool tcp = s->use_tc;
+  DevBuf& featp = s->kpxy;  // (tcgen05 path) split planes of conv4b's output: operand of convPa and convDa
+  if (tcp) {
+    B2_CUDA(ctx, featp.ensure((size_t)Hc * Wc * 128 * sizeof(float)));
+    __half* p0 = s->a0.as<__half>();
+    B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, p0, p0 + px * 64);
+    B2_CHECK_LAUNCH(ctx);
+    // encoder (superpoint.py:148-158) as TMA-fed tcgen05 implicit GEMMs on split-fp16 planes; pools fused
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 1, H, W, true, &s->a1, nullptr))) return rc;      // conv1b + pool
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a1, 2, H2, W2, false, &s->a0, nullptr))) return rc;   // conv2a
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 3, H2, W2, true, &s->a1, nullptr))) return rc;    // conv2b + pool
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a1, 4, H4, W4, false, &s->a0, nullptr))) return rc;   // conv3a
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 5, H4, W4, true, &s->a1, nullptr))) return rc;    // conv3b + pool
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a1, 6, Hc, Wc, false, &s->a0, nullptr))) return rc;   // conv4a
+    if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 7, Hc, Wc, false, &featp, feat))) return rc;      // conv4b (planes + fp32)
+    if ((rc = sp_conv3x3_tc(ctx, st, featp, 8, Hc, Wc, false, nullptr, head))) return rc;     // convPa -> fp32 for the score head
+  } else {
+  B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, (__half*)nullptr,
+            (__half*)nullptr);
+  B2_CHECK_LAUNCH(ctx);
   // encoder (superpoint.py:148-158); pools fused into conv1b / conv2b / conv3b
   if ((rc = sp_conv3x3(ctx, st, a0, 1, a1, H, W, true))) return rc;      // conv1b + pool -> (H2, W2, 64) in a1
   if ((rc = sp_conv3x3(ctx, st, a1, 2, a0, H2, W2, false))) return rc;   // conv2a
@@ -606,6 +701,7 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   if ((rc = sp_conv3x3(ctx, st, a0, 7, feat, Hc, Wc, false))) return rc; // conv4b
   // detector head (superpoint.py:161-167)
   if ((rc = sp_conv3x3(ctx, st, feat, 8, head, Hc, Wc, false))) return rc;  // convPa
+  }
   B2_LAUNCH(ctx, k_head_scores, cdiv(Hc * Wc, PB_CELLS), 128, 0, st, head, s->w[9], s->b[9], s->heat.as<float>(), Hc, Wc);
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaMemsetAsync(s->rowcnt.p, 0, (size_t)(H8 + 1) * sizeof(int), st));
@@ -618,12 +714,19 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
             out_score, cap);
   B2_CHECK_LAUNCH(ctx);
   // descriptor head (superpoint.py:190-192): dense map stays resident for the describe stage
-  if ((rc = sp_conv3x3(ctx, st, feat, 10, head, Hc, Wc, false))) return rc;  // convDa
+  if (tcp) {
+    if ((rc = sp_conv3x3_tc(ctx, st, featp, 10, Hc, Wc, false, nullptr, head))) return rc;  // convDa
+  } else if ((rc = sp_conv3x3(ctx, st, feat, 10, head, Hc, Wc, false))) return rc;  // convDa
   B2_LAUNCH(ctx, k_head_desc, cdiv(Hc * Wc, DB_CELLS), 256, 0, st, head, s->w[11], s->b[11], s->dense.as<float>(), Hc * Wc);
   B2_CHECK_LAUNCH(ctx);
   int n = 0;
   B2_CUDA(ctx, cudaMemcpyAsync(&n, s->rowoff.as<int>() + H8, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
+  if (tcp) {
+    int err = 0;
+    B2_CUDA(ctx, cudaMemcpy(&err, s->errflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return b2_fail(ctx, B2_ERR_STATE, "tcgen05 conv pipeline timed out on an mbarrier (kernel bug)");
+  }
   s->n_kp = n;
   s->have_dense = true;
   *out_n = n;
