@@ -219,15 +219,17 @@ def run_cuda(args):
     stats = {"matches": 0, "inliers": 0, "pairs": 0}
 
     def step_device(c):
+        pending = []
         for j in range(NEW_FRAMES):
             f = fe.detect(frames_dev[c + j])
             for prev in list(window):
                 m, _ = fe.match(prev, f)
-                _, _, _, ninl, _ = fe.verify(prev, f, m, cal, cal, THR_PX)
+                pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next pair's matcher kernels
                 stats["matches"] += int(m.shape[0])
-                stats["inliers"] += ninl
                 stats["pairs"] += 1
             window.append(f)
+        for fut in pending:  # every verification result is collected inside the step
+            stats["inliers"] += fut.result()[3]
 
     for _ in range(args.warmup):
         step_device(cursor)
@@ -243,6 +245,7 @@ def run_cuda(args):
     barrier()
     sampler.start()
     launches0 = fe.ctx.launch_count()
+    vlaunch0 = fe._vctx.launch_count() if fe._vctx else 0
     fe.ctx.profile_start(DOMINANT_KERNEL)
     total_ms = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,7 +259,18 @@ def run_cuda(args):
         total_ms += e0.elapsed_time(e1)
         cursor += NEW_FRAMES
     k_ms, k_launches, k_flop = fe.ctx.profile_stop()
-    launches = fe.ctx.launch_count() - launches0
+    launches = fe.ctx.launch_count() - launches0 + (fe._vctx.launch_count() - vlaunch0 if fe._vctx else 0)
+    # secondary figures (untimed region): detect-only rate (BASELINE configs[1] shape) and the encoder convolutions' rate
+    torch.cuda.synchronize()
+    fe.ctx.profile_start("k_conv_tma")
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for j in range(16):
+        fe.detect(frames_dev[j % len(frames_dev)])
+    d1.record()
+    torch.cuda.synchronize()
+    conv_ms, conv_n, conv_flop = fe.ctx.profile_stop()
+    detect_ips = 16.0 / (d0.elapsed_time(d1) / 1e3)
     barrier()
     clocks = sampler.stop()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -323,6 +337,10 @@ def run_cuda(args):
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_launches / args.steps,
                          "kernel_share_of_step": k_ms / total_ms if total_ms else None},
             "work": {"matches_per_pair": stats["matches"] / max(1, stats["pairs"]), "inliers_per_pair": stats["inliers"] / max(1, stats["pairs"])},
+            "extra": {"superpoint_detect_describe_images_per_sec_1gpu": detect_ips,
+                      "encoder_conv_tflops": (conv_flop / 1e12) / (conv_ms / 1e3) if conv_ms > 0 else None,
+                      "encoder_conv_frac_of_measured_bf16": ((conv_flop / 1e12) / (conv_ms / 1e3)) / tf_peak if conv_ms > 0 else None,
+                      "note": "split-fp16 x3 products: tensor-pipe FLOPs are 3x the algorithmic FLOPs reported here"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = best_cpu_threads(frames)

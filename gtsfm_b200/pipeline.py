@@ -45,6 +45,11 @@ class DeviceFrontEnd:
             blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
             self.ctx.check(self.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
         self._scratch: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+        # verification runs on its own context + stream + host thread so that the (latency-bound, 16-CTA) RANSAC kernels of
+        # pair p overlap the matcher kernels of pair p+1 (ctypes calls release the GIL)
+        self._vctx: Optional[_lib.Context] = None
+        self._vstream: Optional[torch.cuda.Stream] = None
+        self._vpool = None
 
     def _stream(self):
         return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -87,9 +92,24 @@ class DeviceFrontEnd:
         self.ctx.check(rc, "lightglue_match_dev")
         return out[: k.value], stop.value
 
+    def verify_async(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1, cal2, threshold_px: float = 4.0,
+                     seed: int = DEFAULT_SEED):
+        """Same as verify() but returns a concurrent.futures.Future; `matches` must already be complete on the device
+        (match() synchronises its stream before returning)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        if self._vpool is None:
+            self._vctx = _lib.Context(self.device.index)
+            self._vstream = torch.cuda.Stream(self.device)
+            self._vpool = ThreadPoolExecutor(max_workers=1)
+        return self._vpool.submit(self.verify, a, b, matches, cal1, cal2, threshold_px, seed, self._vctx, self._vstream)
+
     def verify(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1: Sequence[float], cal2: Sequence[float],
-               threshold_px: float = 4.0, seed: int = DEFAULT_SEED):
+               threshold_px: float = 4.0, seed: int = DEFAULT_SEED, ctx: Optional[_lib.Context] = None,
+               stream: Optional[torch.cuda.Stream] = None):
         """cal = (f, u0, v0).  -> (E (3,3) | None, R, t, num_inliers, mask device tensor)."""
+        ctx = ctx or self.ctx
+        sptr = _lib.C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
         k = int(matches.shape[0])
         mask = torch.zeros(max(k, 1), dtype=torch.uint8, device=self.device)
         if k < 6:  # opencv_verifier_base.py:70-79
@@ -98,10 +118,10 @@ class DeviceFrontEnd:
         c1, c2 = np.asarray(cal1, np.float64), np.asarray(cal2, np.float64)
         n = _lib.C.c_int(0)
         prm = _lib.RansacParams(threshold_px / max(c1[0], c2[0]), RANSAC_SUCCESS_PROB, E_MAX_ITERS, seed)
-        rc = self.lib.b2_ransac_essential_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(b.kp), _lib.ptr(matches.contiguous()), k, _lib.ptr(c1),
+        rc = self.lib.b2_ransac_essential_dev(ctx.handle, _lib.ptr(a.kp), _lib.ptr(b.kp), _lib.ptr(matches.contiguous()), k, _lib.ptr(c1),
                                               _lib.ptr(c2), _lib.C.byref(prm), _lib.ptr(E), _lib.ptr(mask), _lib.C.byref(n), _lib.ptr(R),
-                                              _lib.ptr(t), self._stream())
-        self.ctx.check(rc, "ransac_essential_dev")
+                                              _lib.ptr(t), sptr)
+        ctx.check(rc, "ransac_essential_dev")
         if rc == 1:
             return None, None, None, 0, mask[:k]
         return E.reshape(3, 3), R.reshape(3, 3), t, n.value, mask[:k]
