@@ -5,10 +5,11 @@
 // One CTA (320 threads, one per SM) owns TWO 128-query tiles of one head and streams a range of 64-key tiles:
 //   warp 8 lane 0 : TMA producer  - Q once, then K / V tiles through 2-stage rings (128-byte swizzled, zero OOB fill)
 //   warp 9        : TMEM allocator (512 columns); lane 0 = MMA issuer.  Per key tile and query tile q:
-//                     S_q  (128 x 64, two fp32 accumulators) = Qh Kh^T ; Qh Kl^T + Ql Kh^T       12 tcgen05.mma
+//                     S_q  (128 x 64, ONE fp32 accumulator, double-buffered; q / k lo planes are unscaled)
+//                                                            = Qh Kh^T + Qh Kl^T + Ql Kh^T       12 tcgen05.mma
 //                     O'_q (128 x 64, two accumulators)      = Ph Vh   ; Ph Vl + Pl Vh           12 tcgen05.mma
-//                   issued in the order PV_0(i), S_0(i+1), PV_1(i), S_1(i+1) so the tensor pipe always has work queued
-//                   while the other query tile is in softmax.
+//                   issued in the order PV_0(i), S_0(i+2), PV_1(i), S_1(i+2): the logits run two key tiles ahead of the
+//                   softmax, so a warpgroup never waits for the tensor pipe in steady state.
 //   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one thread per query row (= TMEM lane): tcgen05.ld S, online
 //                   softmax in base 2 entirely in registers, P = 2^(s - m) split to fp16 hi / lo and stored (128-byte
 //                   swizzled) as the next A operand, O = (O + O'_{i-1}) * 2^(m_old - m_new) folded in one tile late so the
@@ -65,10 +66,10 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
   uint64_t* k_empty = bars + 3;     // [2]
   uint64_t* v_full = bars + 5;      // [2]
   uint64_t* v_empty = bars + 7;     // [2]
-  uint64_t* s_full = bars + 9;      // [2] per query tile
-  uint64_t* p_full = bars + 11;     // [2]
-  uint64_t* o_full = bars + 13;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* s_full = bars + 9;      // [4] query tile x logits buffer
+  uint64_t* p_full = bars + 13;     // [2]
+  uint64_t* o_full = bars + 15;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int z = blockIdx.z / args.nsplit, split = blockIdx.z % args.nsplit;
@@ -86,7 +87,7 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
     tc::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&k_full[i], 1), tc::mbar_init(&k_empty[i], 1), tc::mbar_init(&v_full[i], 1), tc::mbar_init(&v_empty[i], 1);
-      tc::mbar_init(&s_full[i], 1), tc::mbar_init(&p_full[i], 128), tc::mbar_init(&o_full[i], 1);
+      tc::mbar_init(&s_full[i], 1), tc::mbar_init(&s_full[2 + i], 1), tc::mbar_init(&p_full[i], 128), tc::mbar_init(&o_full[i], 1);
     }
     tc::fence_mbar_init();
   }
@@ -123,20 +124,20 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
       // ===== MMA issuer =====
       const uint32_t idS = tc::idesc_f16(AW_Q, AW_KV);                        // Q K^T: both K-major
       const uint32_t idO = tc::idesc_f16(AW_Q, AW_D) | tc::IDESC_B_MN_MAJOR;  // P V: V as stored = MN-major
-      auto issue_S = [&](int q, int s) {
+      auto issue_S = [&](int q, int s, int buf) {
         const uint64_t dQh = tc::smem_desc_sw128(smem0 + AW_OFF_Q + (2 * q) * AW_Q_BYTES);
         const uint64_t dQl = tc::smem_desc_sw128(smem0 + AW_OFF_Q + (2 * q + 1) * AW_Q_BYTES);
         const uint64_t dKh = tc::smem_desc_sw128(smem0 + AW_OFF_K + (2 * s) * AW_KV_BYTES);
         const uint64_t dKl = tc::smem_desc_sw128(smem0 + AW_OFF_K + (2 * s + 1) * AW_KV_BYTES);
-        const uint32_t tS0 = tmem + q * 256, tS1 = tS0 + 64;
+        const uint32_t tS = tmem + q * 256 + buf * 64;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 2);  // 16 dims = 32 bytes
-          tc::umma_f16(tS0, dQh + adv, dKh + adv, idS, ks ? 1u : 0u);
-          tc::umma_f16(tS1, dQh + adv, dKl + adv, idS, ks ? 1u : 0u);
-          tc::umma_f16(tS1, dQl + adv, dKh + adv, idS, 1u);
+          tc::umma_f16(tS, dQh + adv, dKh + adv, idS, ks ? 1u : 0u);
+          tc::umma_f16(tS, dQh + adv, dKl + adv, idS, 1u);  // unscaled lo planes: all three products share the accumulator
+          tc::umma_f16(tS, dQl + adv, dKh + adv, idS, 1u);
         }
-        tc::umma_commit(&s_full[q]);
+        tc::umma_commit(&s_full[q * 2 + buf]);
       };
       auto issue_PV = [&](int q, int s) {
         const uint64_t dPh = tc::smem_desc_sw128(smem0 + AW_OFF_P + (2 * q) * AW_Q_BYTES);
@@ -157,22 +158,29 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
       ok = tc::mbar_wait(q_full, 0) && ok;
       ok = tc::mbar_wait(&k_full[0], 0) && ok;
       tc::fence_after_sync();
-      issue_S(0, 0);
-      issue_S(1, 0);
+      issue_S(0, 0, 0);
+      issue_S(1, 0, 0);
       tc::umma_commit(&k_empty[0]);
+      if (T > 1) {
+        ok = tc::mbar_wait(&k_full[1], 0) && ok;
+        tc::fence_after_sync();
+        issue_S(0, 1, 1);
+        issue_S(1, 1, 1);
+        tc::umma_commit(&k_empty[1]);
+      }
       for (int i = 0; i < T; ++i) {
-        const int sv = i & 1, sk = (i + 1) & 1;
-        const bool more = i + 1 < T;
+        const int sv = i & 1;           // V stage of tile i; also the K stage and logits buffer of tile i + 2
+        const bool more = i + 2 < T;
         ok = tc::mbar_wait(&v_full[sv], (i >> 1) & 1) && ok;
-        if (more) ok = tc::mbar_wait(&k_full[sk], ((i + 1) >> 1) & 1) && ok;
+        if (more) ok = tc::mbar_wait(&k_full[sv], ((i + 2) >> 1) & 1) && ok;
         for (int q = 0; q < 2; ++q) {
-          ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) in smem; S_q(i) and O'_q(i-1) consumed
+          ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) in smem; logits buffer i & 1 and O'_q(i-1) consumed
           tc::fence_after_sync();
           issue_PV(q, sv);
-          if (more) issue_S(q, sk);
+          if (more) issue_S(q, sv, sv);
         }
         tc::umma_commit(&v_empty[sv]);
-        if (more) tc::umma_commit(&k_empty[sk]);
+        if (more) tc::umma_commit(&k_empty[sv]);
       }
     }
   } else {
@@ -180,7 +188,7 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
     const int q = warp >> 2;
     const int r = t & 127;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS0 = tmem + q * 256 + lane_off, tS1 = tS0 + 64, tO0 = tS0 + 128, tO1 = tS0 + 192;
+    const uint32_t tSb = tmem + q * 256 + lane_off, tO0 = tSb + 128, tO1 = tSb + 192;
     unsigned char* sPh = sm + AW_OFF_P + (2 * q) * AW_Q_BYTES;
     unsigned char* sPl = sPh + AW_Q_BYTES;
     const float c2 = args.scale * 1.4426950408889634f;
@@ -190,22 +198,22 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
 
     for (int i = 0; i < T; ++i) {
-      ok = tc::mbar_wait(&s_full[q], i & 1) && ok;
+      ok = tc::mbar_wait(&s_full[q * 2 + (i & 1)], (i >> 1) & 1) && ok;
       tc::fence_after_sync();
+      const uint32_t tS = tSb + (i & 1) * 64;
       const int k0 = (tile0 + i) * AW_KV;
       const bool ragged = k0 + AW_KV > Nk;
       float mx = -INFINITY;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
-        float a0[32], a1[32];
-        tc::tmem_ld32(tS0 + cc * 32, a0);
-        tc::tmem_ld32(tS1 + cc * 32, a1);
+        float a0[32];
+        tc::tmem_ld32(tS + cc * 32, a0);
         if (!ragged) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(a1[j], tc::LO_INV, a0[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, a0[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (k0 + cc * 32 + j < Nk) ? fmaf(a1[j], tc::LO_INV, a0[j]) : -INFINITY);
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (k0 + cc * 32 + j < Nk) ? a0[j] : -INFINITY);
         }
       }
       const float m_new = fmaxf(m_i, mx * c2);
@@ -214,14 +222,13 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ws(const __grid_
       float rs = 0.f;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        float a0[32], a1[32];
-        tc::tmem_ld32(tS0 + cc * 32, a0);
-        tc::tmem_ld32(tS1 + cc * 32, a1);
+        float a0[32];
+        tc::tmem_ld32(tS + cc * 32, a0);
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int j = 2 * jj;
-          float pa = tc::ex2(fmaf(fmaf(a1[j], tc::LO_INV, a0[j]), c2, -m_new));
-          float pb = tc::ex2(fmaf(fmaf(a1[j + 1], tc::LO_INV, a0[j + 1]), c2, -m_new));
+          float pa = tc::ex2(fmaf(a0[j], c2, -m_new));
+          float pb = tc::ex2(fmaf(a0[j + 1], c2, -m_new));
           if (ragged) {
             if (k0 + cc * 32 + j >= Nk) pa = 0.f;
             if (k0 + cc * 32 + j + 1 >= Nk) pb = 0.f;

@@ -40,6 +40,7 @@ struct GemmTcArgs {
   int ldch;        // row-major leading dimension of Ch / Cl (ignored when head_major)
   int head_major;  // 1: Ch / Cl (and C) are written as [N/64][M][64] (attention head layout)
   int relu;        // max(., 0) after bias / scale, before the residual
+  int lo_unscaled; // split outputs keep lo = fp16(x - hi)
   int* err_flag;   // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
   long long* timing;  // debug: clock64 stamps of CTA (0,0,0) (null in production)
 };
@@ -202,7 +203,8 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
             if (cp) cp[(size_t)r * str_c] = v;
             if (hp) {
               __half hh, ll;
-              tc::split_h(v, hh, ll);
+              if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
+              else tc::split_h(v, hh, ll);
               hp[(size_t)r * str_s] = hh;
               lp[(size_t)r * str_s] = ll;
             }
@@ -216,7 +218,8 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tc(GemmTcArgs g) {
           if (cp) cp[(size_t)r * str_c] = v;
           if (hp) {
             __half hh, ll;
-            tc::split_h(v, hh, ll);
+            if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
+            else tc::split_h(v, hh, ll);
             hp[(size_t)r * str_s] = hh;
             lp[(size_t)r * str_s] = ll;
           }

@@ -37,6 +37,7 @@ struct GemmTmaArgs {
   int ldr;
   float scale;
   int ldc, ldch, head_major, relu;
+  int lo_unscaled;  // split outputs keep lo = fp16(x - hi) (attention q / k operands of k_flash_ws)
   int* err_flag;
 };
 
@@ -185,7 +186,8 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tma(const __grid_constan
             if (cp) cp[(size_t)r * str_c] = v;
             if (hp) {
               __half hh, ll;
-              tc::split_h(v, hh, ll);
+              if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
+              else tc::split_h(v, hh, ll);
               hp[(size_t)r * str_s] = hh;
               lp[(size_t)r * str_s] = ll;
             }
@@ -199,7 +201,8 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tma(const __grid_constan
           if (cp) cp[(size_t)r * str_c] = v;
           if (hp) {
             __half hh, ll;
-            tc::split_h(v, hh, ll);
+            if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
+            else tc::split_h(v, hh, ll);
             hp[(size_t)r * str_s] = hh;
             lp[(size_t)r * str_s] = ll;
           }

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict__ qkv, const float* __restrict__ cs,
                                                           const float* __restrict__ sn, int n, size_t plane,
-                                                          void* __restrict__ qo, void* __restrict__ ko, void* __restrict__ vo) {
+                                                          void* __restrict__ qo, void* __restrict__ ko, void* __restrict__ vo,
+                                                          int qk_unscaled) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n * 4 * 32 pairs
   if (i >= n * 128) return;
   int p = i & 31, h = (i >> 5) & 3, r = i >> 7;
@@ -137,8 +138,13 @@ __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       __half ha, la, hb, lb;
-      tc::split_h(va[j], ha, la);
-      tc::split_h(vb[j], hb, lb);
+      if (qk_unscaled && j < 2) {  // q, k feed the single-accumulator logits product
+        tc::split_h_unscaled(va[j], ha, la);
+        tc::split_h_unscaled(vb[j], hb, lb);
+      } else {
+        tc::split_h(va[j], ha, la);
+        tc::split_h(vb[j], hb, lb);
+      }
       *reinterpret_cast<__half2*>(outs[j] + o) = __halves2half2(ha, hb);
       *reinterpret_cast<__half2*>(outs[j] + plane + o) = __halves2half2(la, lb);
     }
@@ -621,10 +627,10 @@ static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, in
     const int n = sd.n;
     if (s->use_tc)
       B2_LAUNCH(ctx, k_lg_split_rotary<true>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p);
+                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, attn_qk_unscaled(lg_tw(s)) ? 1 : 0);
     else
       B2_LAUNCH(ctx, k_lg_split_rotary<false>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p);
+                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, 0);
     B2_CHECK_LAUNCH(ctx);
   }
   LgSide &a = s->side[0], &b = s->side[1];
@@ -646,6 +652,7 @@ static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, i
       a.w = which ? w.wv : w.wqk, a.ldb = 256, a.bias = which ? w.bv : w.bqk;
       DevBuf& dst = which ? sd.v : sd.q;
       a.cf = dst.as<float>(), a.cp = planes_of(dst, e), a.head_major = 1, a.M = sd.n, a.N = 256;
+      a.lo_unscaled = (which == 0 && attn_qk_unscaled(lg_tw(s))) ? 1 : 0;  // to_qk output = logits operand
     }
     if ((rc = lg_linear(ctx, st, s, p[0], &p[1]))) return rc;
   }

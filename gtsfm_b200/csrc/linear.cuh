@@ -20,6 +20,9 @@ struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (s
   int sm_count = 148;
 };
 
+// q / k planes feed the warp-specialised attention (single logits accumulator) with an UNSCALED lo plane
+static inline bool attn_qk_unscaled(const TcWeights& tw) { return tw.use_tc && tw.use_tma && tw.attn_part && tma_encoder() != nullptr; }
+
 struct Pl {  // split-fp16 planes of an activation
   __half* hi;
   __half* lo;
@@ -50,6 +53,7 @@ struct LinArgs {
   int head_major = 0;
   bool tc_want_f32 = false;
   int relu = 0;  // max(., 0) after bias / scale, before the residual
+  int lo_unscaled = 0;  // plane output with an unscaled lo plane (q / k operands of the warp-specialised attention)
   int M = 0, N = 0;
 };
 
@@ -101,7 +105,7 @@ static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     ok = ok && tma_map_2d(&maps.bh, bh, a.N, a.K1 + a.K2, a.ldb, TM_N) && tma_map_2d(&maps.bl, bl, a.N, a.K1 + a.K2, a.ldb, TM_N);
     if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     q.K1 = a.K1, q.K2 = a.K2, q.N = a.N, q.bias = a.bias, q.ldr = a.ldr, q.scale = a.scale, q.ldc = a.ldc, q.ldch = a.ldch;
-    q.head_major = a.head_major, q.relu = a.relu, q.err_flag = tw.err;
+    q.head_major = a.head_major, q.relu = a.relu, q.lo_unscaled = a.lo_unscaled, q.err_flag = tw.err;
     dim3 grid(cdiv(a.N, TM_N), cdiv(maxM, TM_M), b ? 2 : 1);
     b2_prof_work(ctx, "k_gemm_tma", work);
     B2_LAUNCH(ctx, k_gemm_tma, grid, 128, TM_GEMM_SMEM, st, maps, q);
@@ -129,7 +133,7 @@ static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     t.Bh = a.bp.hi, t.Bl = a.bp.lo;
   }
   t.ldb = a.ldb, t.N = a.N, t.bias = a.bias, t.ldr = a.ldr, t.scale = a.scale, t.ldc = a.ldc, t.ldch = a.ldch;
-  t.head_major = a.head_major, t.relu = a.relu, t.err_flag = tw.err;
+  t.head_major = a.head_major, t.relu = a.relu, t.lo_unscaled = a.lo_unscaled, t.err_flag = tw.err;
   dim3 grid(cdiv(a.N, TC_N), cdiv(maxM, TC_M), b ? 2 : 1);
   b2_prof_work(ctx, "k_gemm_tc", work);
   B2_LAUNCH(ctx, k_gemm_tc, grid, 128, TC_GEMM_SMEM, st, t);

@@ -117,6 +117,13 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
 }
+// variant with the lo plane left unscaled (lo = fp16(x - hi)): lets hi*hi + hi*lo + lo*hi share ONE accumulator.  Used for
+// the attention logits' operands (q, k are O(1): lo only turns subnormal below |x| < 0.25, where its absolute error
+// <= 3e-8 is far under the logits' own fp32 rounding).
+__device__ __forceinline__ void split_h_unscaled(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
 // 8 consecutive floats -> two 16-byte chunks (hi, lo)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   __half h[8], l[8];
