@@ -1,0 +1,300 @@
+// Warp-specialised tcgen05 + TMA flash attention, A operands in TMEM ("TS" MMAs), split-fp16 operands (~fp32 accuracy).
+//
+//   O[Nq][256] = softmax(scale * Q K^T) V per head; q / k / v arrive as fp16 hi / lo planes with UNSCALED lo
+//   (x ~= hi + lo, lo = fp16(x - hi)), the output leaves as hi / lo planes with the usual 2^11-scaled lo.
+//
+// Why TMEM operands: a 128 x 64 x 16 SS-mode MMA reads 4 KB of A and 2 KB of B from shared memory per 32 tensor cycles
+// (192 B/clk > the 128 B/clk the SM's shared memory delivers), so the smem-operand version of this kernel (attn_ws.cuh)
+// is shared-memory-bound at ~2x the tensor time (ncu: tensor pipe 24 % active).  Here Q lives in TMEM for the whole CTA
+// and P is written back over its own logits in TMEM, so shared memory only carries the K / V tiles (B operands).
+//
+// One CTA (320 threads, one per SM) owns TWO 128-query tiles of one head and streams a range of 64-key tiles.
+// TMEM (512 columns; per query tile q at q * 256):
+//     [  0, 64) logits buffer 0: S (128 x 64 fp32), overwritten in place by P: hi = columns [0, 32), lo = [32, 64)
+//     [ 64,128) logits buffer 1                                                 (column c = keys 2c, 2c + 1 as half2)
+//     [128,192) O accumulator (128 x 64 fp32), accumulated by the tensor core across ALL key tiles
+//     [192,224) Q hi, [224,256) Q lo  (column c = dims 2c, 2c + 1)
+//   warp 8 lane 0 : TMA producer - K and V tiles through two 4-stage rings (128-byte swizzled, zero OOB fill)
+//   warp 9        : TMEM allocator; lane 0 = MMA issuer.  Per key tile i and query tile q, in the order
+//                     PV_q(i): O_q += Ph Vh + Ph Vl + Pl Vh   (A = P from TMEM, B = V MN-major)      12 tcgen05.mma
+//                     S_q(i+2) = Qh Kh^T + Qh Kl^T + Ql Kh^T  (A = Q from TMEM) into buffer i & 1    12 tcgen05.mma
+//                   the logits run two key tiles ahead of the softmax.
+//   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one thread per query row (= TMEM lane): tcgen05.ld S, base-2
+//                   online softmax with a LAZY reference maximum (O and l are only rescaled when the row maximum grew by
+//                   more than 2^8 - P then stays <= 256, exact in the hi / lo split - so O normally never leaves TMEM),
+//                   P = 2^(s - m) split to fp16 hi / lo and stored over S with tcgen05.st.
+// Hand-offs are mbarriers: TMA complete_tx (k_full, v_full), tcgen05.commit (s_full, o_full, k_empty, v_empty) and
+// 128-thread arrivals (q_ready, p_full).  With `nsplit` > 1 a CTA covers a slice of the key range and writes un-normalised
+// partials (O, m, l) that k_attn_merge combines.
+#pragma once
+#include "attn_ws.cuh"
+
+constexpr int AS_NK = 4, AS_NV = 4;                       // ring depths
+constexpr int AS_STAGE = 2 * AW_KV_BYTES;                 // hi + lo plane of one 64 x 64 tile = 16 KB
+constexpr int AS_OFF_K = 0, AS_OFF_V = AS_NK * AS_STAGE;  // 64 KB each
+constexpr int AS_TILE_BYTES = AS_OFF_V + AS_NV * AS_STAGE;
+constexpr size_t AS_SMEM = AS_TILE_BYTES + 1024 + 512;
+constexpr uint32_t AS_COL_O = 128, AS_COL_Q = 192;
+constexpr float AS_RESCALE = 8.0f;  // log2 of the largest P allowed before the reference maximum is refreshed
+
+struct AttnTsMaps {
+  CUtensorMap kh[2], kl[2], vh[2], vl[2];  // per problem; 2-D views [4 * N rows][64] of the head-major planes
+};
+struct AttnTsProblem {
+  const __half *Qh, *Ql;  // head-major planes [4][Nq][64]
+  __half *Oh, *Ol;        // final output planes [Nq][256] (column h * 64 + d)            (nsplit == 1)
+  float* Opart;           // partial O   [nsplit][Nq][256] fp32, un-normalised            (nsplit > 1)
+  float* ml;              // partial m,l [nsplit][4][Nq][2]
+  int Nq, Nk;
+};
+struct AttnTsArgs {
+  AttnTsProblem p[2];
+  float scale;
+  int nsplit;
+  int* err_flag;
+};
+
+static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_constant__ AttnTsMaps maps, AttnTsArgs args) {
+  extern __shared__ unsigned char as_raw[];
+  const uint32_t raw = tc::smem_u32(as_raw);
+  const uint32_t smem0 = (raw + 1023u) & ~1023u;
+  unsigned char* sm = as_raw + (smem0 - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AS_TILE_BYTES);
+  uint64_t* k_full = bars;                  // [AS_NK]
+  uint64_t* k_empty = k_full + AS_NK;       // [AS_NK]
+  uint64_t* v_full = k_empty + AS_NK;       // [AS_NV]
+  uint64_t* v_empty = v_full + AS_NV;       // [AS_NV]
+  uint64_t* s_full = v_empty + AS_NV;       // [4] query tile x logits buffer
+  uint64_t* p_full = s_full + 4;            // [2]
+  uint64_t* o_full = p_full + 2;            // [2]
+  uint64_t* q_ready = o_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 2);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int z = blockIdx.z / args.nsplit, split = blockIdx.z % args.nsplit;
+  const AttnTsProblem& pr = args.p[z];
+  const int Nq = pr.Nq, Nk = pr.Nk;
+  const int h = blockIdx.y, q0 = blockIdx.x * (2 * AW_Q);
+  if (q0 >= Nq) return;  // uniform
+  const int tiles_total = (Nk + AW_KV - 1) / AW_KV;
+  const int per = (tiles_total + args.nsplit - 1) / args.nsplit;
+  const int tile0 = split * per, tile1 = min(tiles_total, tile0 + per);
+  const int T = tile1 - tile0;  // may be <= 0 for a trailing split: then this CTA writes neutral partials
+
+  if (t == 0) {
+    for (int i = 0; i < AS_NK; ++i) tc::mbar_init(&k_full[i], 1), tc::mbar_init(&k_empty[i], 1);
+    for (int i = 0; i < AS_NV; ++i) tc::mbar_init(&v_full[i], 1), tc::mbar_init(&v_empty[i], 1);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&p_full[i], 128), tc::mbar_init(&o_full[i], 1), tc::mbar_init(&q_ready[i], 128);
+    tc::fence_mbar_init();
+  }
+  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  bool ok = true;
+
+  if (warp == 8) {
+    if (lane == 0 && T > 0) {
+      // ===== TMA producer: K(0), K(1), then V(i), K(i+2) in the order the issuer consumes them =====
+      auto load_k = [&](int j) {
+        const int s = j % AS_NK;
+        if (j >= AS_NK) ok = tc::mbar_wait(&k_empty[s], ((j / AS_NK) - 1) & 1) && ok;
+        tc::mbar_expect_tx(&k_full[s], AS_STAGE);
+        const int row = h * Nk + (tile0 + j) * AW_KV;
+        tc::tma_load_2d(smem0 + AS_OFF_K + s * AS_STAGE, &maps.kh[z], &k_full[s], 0, row);
+        tc::tma_load_2d(smem0 + AS_OFF_K + s * AS_STAGE + AW_KV_BYTES, &maps.kl[z], &k_full[s], 0, row);
+      };
+      auto load_v = [&](int j) {
+        const int s = j % AS_NV;
+        if (j >= AS_NV) ok = tc::mbar_wait(&v_empty[s], ((j / AS_NV) - 1) & 1) && ok;
+        tc::mbar_expect_tx(&v_full[s], AS_STAGE);
+        const int row = h * Nk + (tile0 + j) * AW_KV;
+        tc::tma_load_2d(smem0 + AS_OFF_V + s * AS_STAGE, &maps.vh[z], &v_full[s], 0, row);
+        tc::tma_load_2d(smem0 + AS_OFF_V + s * AS_STAGE + AW_KV_BYTES, &maps.vl[z], &v_full[s], 0, row);
+      };
+      load_k(0);
+      if (T > 1) load_k(1);
+      for (int i = 0; i < T; ++i) {
+        load_v(i);
+        if (i + 2 < T) load_k(i + 2);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0 && T > 0) {
+      // ===== MMA issuer =====
+      const uint32_t idS = tc::idesc_f16(AW_Q, AW_KV);                        // Q K^T: A (TMEM) and B K-major
+      const uint32_t idO = tc::idesc_f16(AW_Q, AW_D) | tc::IDESC_B_MN_MAJOR;  // P V: V as stored = MN-major
+      auto issue_S = [&](int q, int j) {  // logits of key tile j into buffer j & 1
+        const int s = j % AS_NK;
+        const uint64_t dKh = tc::smem_desc_sw128(smem0 + AS_OFF_K + s * AS_STAGE);
+        const uint64_t dKl = tc::smem_desc_sw128(smem0 + AS_OFF_K + s * AS_STAGE + AW_KV_BYTES);
+        const uint32_t tS = tmem + q * 256 + (j & 1) * 64;
+        const uint32_t tQh = tmem + q * 256 + AS_COL_Q, tQl = tQh + 32;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);  // 16 dims = 32 bytes of K's rows
+          const uint32_t ac = (uint32_t)(ks * 8);   // 16 dims = 8 TMEM columns of Q
+          tc::umma_f16_ts(tS, tQh + ac, dKh + adv, idS, ks ? 1u : 0u);
+          tc::umma_f16_ts(tS, tQh + ac, dKl + adv, idS, 1u);
+          tc::umma_f16_ts(tS, tQl + ac, dKh + adv, idS, 1u);
+        }
+        tc::umma_commit(&s_full[q * 2 + (j & 1)]);
+      };
+      auto issue_PV = [&](int q, int j) {
+        const int s = j % AS_NV;
+        const uint64_t dVh = tc::smem_desc_sw128_mn(smem0 + AS_OFF_V + s * AS_STAGE);
+        const uint64_t dVl = tc::smem_desc_sw128_mn(smem0 + AS_OFF_V + s * AS_STAGE + AW_KV_BYTES);
+        const uint32_t tPh = tmem + q * 256 + (j & 1) * 64, tPl = tPh + 32;
+        const uint32_t tO = tmem + q * 256 + AS_COL_O;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ac = (uint32_t)(ks * 8);      // 16 keys = 8 TMEM columns of P
+          const uint64_t advV = (uint64_t)(ks * 128);  // 16 keys = two 8-row groups of V = 2048 bytes
+          tc::umma_f16_ts(tO, tPh + ac, dVh + advV, idO, (j | ks) ? 1u : 0u);
+          tc::umma_f16_ts(tO, tPh + ac, dVl + advV, idO, 1u);
+          tc::umma_f16_ts(tO, tPl + ac, dVh + advV, idO, 1u);
+        }
+        tc::umma_commit(&o_full[q]);
+      };
+      ok = tc::mbar_wait(&q_ready[0], 0) && ok;
+      ok = tc::mbar_wait(&q_ready[1], 0) && ok;
+      for (int j = 0; j < 2 && j < T; ++j) {
+        ok = tc::mbar_wait(&k_full[j], 0) && ok;
+        tc::fence_after_sync();
+        issue_S(0, j);
+        issue_S(1, j);
+        tc::umma_commit(&k_empty[j]);
+      }
+      for (int i = 0; i < T; ++i) {
+        const int j2 = i + 2;
+        const bool more = j2 < T;
+        ok = tc::mbar_wait(&v_full[i % AS_NV], (i / AS_NV) & 1) && ok;
+        if (more) ok = tc::mbar_wait(&k_full[j2 % AS_NK], (j2 / AS_NK) & 1) && ok;
+        for (int q = 0; q < 2; ++q) {
+          ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) stored over S_q(i); O_q rescaled if it had to be
+          tc::fence_after_sync();
+          issue_PV(q, i);
+          if (more) issue_S(q, j2);  // overwrites buffer i & 1 = P_q(i): in issue order after PV_q(i) has read it
+        }
+        tc::umma_commit(&v_empty[i % AS_NV]);
+        if (more) tc::umma_commit(&k_empty[j2 % AS_NK]);
+      }
+    }
+  } else {
+    // ===== softmax warpgroups: q = 0 (warps 0-3), q = 1 (warps 4-7); thread = query row = TMEM lane =====
+    const int q = warp >> 2;
+    const int r = t & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tB = tmem + q * 256 + lane_off, tO = tB + AS_COL_O;
+    const int qrow = q0 + q * AW_Q + r;
+    const float c2 = args.scale * 1.4426950408889634f;
+    float m_ref = -INFINITY, l_i = 0.f;
+    float o[64];
+
+    if (T > 0) {
+      // this thread's query row -> TMEM (zero rows past the end)
+      uint32_t w[32];
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const __half* src = (pl ? pr.Ql : pr.Qh) + ((size_t)h * Nq + qrow) * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (qrow < Nq) v = __ldg(reinterpret_cast<const uint4*>(src) + c);
+          w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+        }
+        tc::tmem_st32(tB + AS_COL_Q + pl * 32, w);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&q_ready[q]);
+    }
+
+    for (int i = 0; i < T; ++i) {
+      ok = tc::mbar_wait(&s_full[q * 2 + (i & 1)], (i >> 1) & 1) && ok;
+      tc::fence_after_sync();
+      const uint32_t tS = tB + (i & 1) * 64;
+      const int k0 = (tile0 + i) * AW_KV;
+      float a[64];
+      tc::tmem_ld64(tS, a);
+      if (k0 + AW_KV > Nk) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (k0 + j >= Nk) a[j] = -INFINITY;  // 2^(-inf) = 0
+      }
+      float mx = a[0];
+#pragma unroll
+      for (int j = 1; j < 64; ++j) mx = fmaxf(mx, a[j]);
+      const float m_new = fmaxf(m_ref, mx * c2);
+      bool waited = false;
+      if (__any_sync(0xffffffffu, m_new - m_ref > AS_RESCALE)) {  // also true on the first tile (m_ref = -inf)
+        const float corr = tc::ex2(m_ref - m_new);
+        l_i *= corr;
+        if (i > 0) {  // bring O (in TMEM) to the new reference; PV_q(i-1) must have landed
+          ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;
+          tc::fence_after_sync();
+          waited = true;
+          tc::tmem_ld64(tO, o);
+          uint32_t ow[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) ow[j] = __float_as_uint(o[j] * corr);
+          tc::tmem_st32(tO, ow);
+          tc::tmem_st32(tO + 32, ow + 32);
+        }
+        m_ref = m_new;
+      }
+      uint32_t ph[32], pl[32];
+      float rs = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const float pa = tc::ex2(fmaf(a[2 * jj], c2, -m_ref));
+        const float pb = tc::ex2(fmaf(a[2 * jj + 1], c2, -m_ref));
+        rs += pa + pb;
+        tc::split2_unscaled(pa, pb, ph[jj], pl[jj]);
+      }
+      l_i += rs;
+      tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
+      tc::tmem_st32(tS + 32, pl);
+      tc::tmem_st_wait();
+      if (i > 0 && !waited) ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;  // consume every phase: keeps parities unambiguous
+      tc::fence_before_sync();
+      tc::mbar_arrive(&p_full[q]);
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    if (T > 0) {
+      ok = tc::mbar_wait(&o_full[q], (T - 1) & 1) && ok;
+      tc::fence_after_sync();
+      tc::tmem_ld64(tO, o);
+    }
+    if (qrow < Nq) {
+      if (args.nsplit == 1) {
+        const float inv = 1.0f / l_i;
+        uint4* dh = reinterpret_cast<uint4*>(pr.Oh + (size_t)qrow * 256 + h * 64);
+        uint4* dl = reinterpret_cast<uint4*>(pr.Ol + (size_t)qrow * 256 + h * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+          dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(pr.Opart + ((size_t)split * Nq + qrow) * 256 + h * 64);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        float* ml = pr.ml + (((size_t)split * 4 + h) * Nq + qrow) * 2;
+        ml[0] = m_ref;  // -inf when this split saw no keys
+        ml[1] = l_i;
+      }
+    }
+  }
+  __syncwarp();
+  if (!ok && args.err_flag) *args.err_flag = 1;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+}

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       __half ha, la, hb, lb;
-      if (qk_unscaled && j < 2) {  // q, k feed the single-accumulator logits product
+      if ((qk_unscaled >> (j < 2 ? 0 : 1)) & 1) {  // bit 0: q, k (single-accumulator logits); bit 1: v (k_flash_ts)
         tc::split_h_unscaled(va[j], ha, la);
         tc::split_h_unscaled(vb[j], hb, lb);
       } else {
@@ -526,6 +526,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   {
     const char* e = getenv("B2_FORCE_SIMT");
     s->use_tc = !(e && e[0] == '1');
@@ -627,7 +628,7 @@ static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, in
     const int n = sd.n;
     if (s->use_tc)
       B2_LAUNCH(ctx, k_lg_split_rotary<true>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, attn_qk_unscaled(lg_tw(s)) ? 1 : 0);
+                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, (attn_qk_unscaled(lg_tw(s)) ? 1 : 0) | (attn_v_unscaled(lg_tw(s)) ? 2 : 0));
     else
       B2_LAUNCH(ctx, k_lg_split_rotary<false>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
                 sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, 0);
@@ -652,7 +653,7 @@ static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, i
       a.w = which ? w.wv : w.wqk, a.ldb = 256, a.bias = which ? w.bv : w.bqk;
       DevBuf& dst = which ? sd.v : sd.q;
       a.cf = dst.as<float>(), a.cp = planes_of(dst, e), a.head_major = 1, a.M = sd.n, a.N = 256;
-      a.lo_unscaled = (which == 0 && attn_qk_unscaled(lg_tw(s))) ? 1 : 0;  // to_qk output = logits operand
+      a.lo_unscaled = (which == 0 ? attn_qk_unscaled(lg_tw(s)) : attn_v_unscaled(lg_tw(s))) ? 1 : 0;  // attention operands
     }
     if ((rc = lg_linear(ctx, st, s, p[0], &p[1]))) return rc;
   }

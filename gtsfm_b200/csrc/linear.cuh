@@ -7,6 +7,8 @@
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
 #include "attn_ws.cuh"
+#include "attn_ts.cuh"
+#include <cstdlib>
 
 struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (same element offsets in all three)
   const float* f;
@@ -22,6 +24,16 @@ struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (s
 
 // q / k planes feed the warp-specialised attention (single logits accumulator) with an UNSCALED lo plane
 static inline bool attn_qk_unscaled(const TcWeights& tw) { return tw.use_tc && tw.use_tma && tw.attn_part && tma_encoder() != nullptr; }
+// the TMEM-operand attention kernel (k_flash_ts, default) also takes v with an unscaled lo plane; B2_ATTN_WS=1 selects
+// the shared-memory-operand kernel (k_flash_ws) instead
+static inline bool attn_use_ts() {
+  static const bool ts = [] {
+    const char* e = getenv("B2_ATTN_WS");
+    return !(e && e[0] == '1');
+  }();
+  return ts;
+}
+static inline bool attn_v_unscaled(const TcWeights& tw) { return attn_qk_unscaled(tw) && attn_use_ts(); }
 
 struct Pl {  // split-fp16 planes of an activation
   __half* hi;
@@ -169,13 +181,19 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
       if (cost < best - 1e-9) best = cost, nsplit = sp;
     }
     bool okm = true;
+    const bool ts = attn_use_ts();
+    AttnTsMaps tmaps;
+    AttnTsArgs ta{};
     for (int i = 0; i < 2; ++i) {
       const FlashJob& j = *jobs[i];
       const Pl q = planes_of(*j.q, (size_t)j.capq * 256), k = planes_of(*j.k, (size_t)j.capk * 256), v = planes_of(*j.v, (size_t)j.capk * 256),
                o = planes_of(*j.o, (size_t)j.capq * 256);
-      okm = okm && tma_map_2d(&maps.qh[i], q.hi, (uint64_t)4 * j.nq, 64, 64, AW_Q) && tma_map_2d(&maps.ql[i], q.lo, (uint64_t)4 * j.nq, 64, 64, AW_Q);
-      okm = okm && tma_map_2d(&maps.kh[i], k.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&maps.kl[i], k.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
-      okm = okm && tma_map_2d(&maps.vh[i], v.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&maps.vl[i], v.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+      CUtensorMap *kh = ts ? &tmaps.kh[i] : &maps.kh[i], *kl = ts ? &tmaps.kl[i] : &maps.kl[i];
+      CUtensorMap *vh = ts ? &tmaps.vh[i] : &maps.vh[i], *vl = ts ? &tmaps.vl[i] : &maps.vl[i];
+      if (!ts)
+        okm = okm && tma_map_2d(&maps.qh[i], q.hi, (uint64_t)4 * j.nq, 64, 64, AW_Q) && tma_map_2d(&maps.ql[i], q.lo, (uint64_t)4 * j.nq, 64, 64, AW_Q);
+      okm = okm && tma_map_2d(kh, k.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(kl, k.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+      okm = okm && tma_map_2d(vh, v.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(vl, v.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
       AttnWsProblem& p = wa.p[i];
       p.Oh = o.hi, p.Ol = o.lo, p.Nq = j.nq, p.Nk = j.nk;
       if (nsplit > 1) {
@@ -183,11 +201,20 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
         B2_CUDA(ctx, tw.attn_ml[i].ensure((size_t)nsplit * 4 * j.nq * 2 * 4));
         p.Opart = tw.attn_part[i].as<float>(), p.ml = tw.attn_ml[i].as<float>();
       }
+      AttnTsProblem& tp = ta.p[i];
+      tp.Qh = q.hi, tp.Ql = q.lo, tp.Oh = p.Oh, tp.Ol = p.Ol, tp.Opart = p.Opart, tp.ml = p.ml, tp.Nq = j.nq, tp.Nk = j.nk;
     }
     if (!okm) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (attention)");
     wa.scale = scale, wa.nsplit = nsplit, wa.err_flag = tw.err;
-    b2_prof_work(ctx, "k_flash_ws", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));
-    B2_LAUNCH(ctx, k_flash_ws, dim3(qt, 4, 2 * nsplit), AW_THREADS, AW_SMEM, st, maps, wa);
+    ta.scale = scale, ta.nsplit = nsplit, ta.err_flag = tw.err;
+    const double flops = 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk);
+    if (ts) {
+      b2_prof_work(ctx, "k_flash_ts", flops);
+      B2_LAUNCH(ctx, k_flash_ts, dim3(qt, 4, 2 * nsplit), AW_THREADS, AS_SMEM, st, tmaps, ta);
+    } else {
+      b2_prof_work(ctx, "k_flash_ws", flops);
+      B2_LAUNCH(ctx, k_flash_ws, dim3(qt, 4, 2 * nsplit), AW_THREADS, AW_SMEM, st, maps, wa);
+    }
     B2_CHECK_LAUNCH(ctx);
     if (nsplit > 1) {
       for (int i = 0; i < 2; ++i) {

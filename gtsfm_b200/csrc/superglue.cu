@@ -334,6 +334,7 @@ extern "C" int b2_superglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   const char* e = getenv("B2_FORCE_SIMT");
   s->use_tc = !(e && e[0] == '1');
@@ -393,7 +394,7 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
         g.a1f = sd.x.as<float>(), g.a1p = PL(sd.xs, sd.n, 256), g.lda1 = 256, g.K1 = 256, g.w = wts[which], g.ldb = 256, g.bias = bs[which];
         DevBuf& dst = which == 0 ? sd.q : (which == 1 ? sd.k : sd.v);
         g.cf = dst.as<float>(), g.cp = PL(dst, sd.n, 256), g.head_major = 1, g.M = sd.n, g.N = 256;
-        g.lo_unscaled = (which < 2 && attn_qk_unscaled(tw)) ? 1 : 0;  // q, k = logits operands
+        g.lo_unscaled = (which < 2 ? attn_qk_unscaled(tw) : attn_v_unscaled(tw)) ? 1 : 0;  // attention operands
       }
       if ((rc = run_linear(ctx, st, tw, p[0], &p[1]))) return rc;
     }
