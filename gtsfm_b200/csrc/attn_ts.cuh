@@ -15,7 +15,7 @@
 //     [128,192) O accumulator (128 x 64 fp32), accumulated by the tensor core across ALL key tiles
 //     [192,224) Q hi, [224,256) Q lo  (column c = dims 2c, 2c + 1)
 //   warp 8 lane 0 : TMA producer - K and V tiles through two 4-stage rings (128-byte swizzled, zero OOB fill)
-//   warp 9        : TMEM allocator; lane 0 = MMA issuer.  Per key tile i and query tile q, in the order
+//   warp 9        : TMEM allocator + MMA issuer (warp-uniform, one elected lane).  Per key tile i and query tile q, in the order
 //                     PV_q(i): O_q += Ph Vh + Ph Vl + Pl Vh   (A = P from TMEM, B = V MN-major)      12 tcgen05.mma
 //                     S_q(i+2) = Qh Kh^T + Qh Kl^T + Ql Kh^T  (A = Q from TMEM) into buffer i & 1    12 tcgen05.mma
 //                   the logits run two key tiles ahead of the softmax.
@@ -52,7 +52,18 @@ struct AttnTsArgs {
   float scale;
   int nsplit;
   int* err_flag;
+#ifdef B2_ATTN_TIMING
+  long long* timing;  // scratch/attn_bench.cu: per-phase clock64 sums of CTA 0
+#endif
 };
+
+#ifdef B2_ATTN_TIMING
+#define AS_T0() long long t_ = clock64()
+#define AS_ACC(slot) do { if (stamp) { const long long n_ = clock64(); tacc[slot] += n_ - t_; t_ = n_; } } while (0)
+#else
+#define AS_T0() do { } while (0)
+#define AS_ACC(slot) do { } while (0)
+#endif
 
 static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_constant__ AttnTsMaps maps, AttnTsArgs args) {
   extern __shared__ unsigned char as_raw[];
@@ -122,8 +133,8 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
       }
     }
   } else if (warp == 9) {
-    if (lane == 0 && T > 0) {
-      // ===== MMA issuer =====
+    if (T > 0) {
+      // ===== MMA issuer: the whole warp runs this with uniform operands, one elected lane issues (tc.cuh) =====
       const uint32_t idS = tc::idesc_f16(AW_Q, AW_KV);                        // Q K^T: A (TMEM) and B K-major
       const uint32_t idO = tc::idesc_f16(AW_Q, AW_D) | tc::IDESC_B_MN_MAJOR;  // P V: V as stored = MN-major
       auto issue_S = [&](int q, int j) {  // logits of key tile j into buffer j & 1
@@ -136,11 +147,11 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 2);  // 16 dims = 32 bytes of K's rows
           const uint32_t ac = (uint32_t)(ks * 8);   // 16 dims = 8 TMEM columns of Q
-          tc::umma_f16_ts(tS, tQh + ac, dKh + adv, idS, ks ? 1u : 0u);
-          tc::umma_f16_ts(tS, tQh + ac, dKl + adv, idS, 1u);
-          tc::umma_f16_ts(tS, tQl + ac, dKh + adv, idS, 1u);
+          tc::umma_f16_ts_w(tS, tQh + ac, dKh + adv, idS, ks ? 1u : 0u);
+          tc::umma_f16_ts_w(tS, tQh + ac, dKl + adv, idS, 1u);
+          tc::umma_f16_ts_w(tS, tQl + ac, dKh + adv, idS, 1u);
         }
-        tc::umma_commit(&s_full[q * 2 + (j & 1)]);
+        tc::umma_commit_w(&s_full[q * 2 + (j & 1)]);
       };
       auto issue_PV = [&](int q, int j) {
         const int s = j % AS_NV;
@@ -152,35 +163,48 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t ac = (uint32_t)(ks * 8);      // 16 keys = 8 TMEM columns of P
           const uint64_t advV = (uint64_t)(ks * 128);  // 16 keys = two 8-row groups of V = 2048 bytes
-          tc::umma_f16_ts(tO, tPh + ac, dVh + advV, idO, (j | ks) ? 1u : 0u);
-          tc::umma_f16_ts(tO, tPh + ac, dVl + advV, idO, 1u);
-          tc::umma_f16_ts(tO, tPl + ac, dVh + advV, idO, 1u);
+          tc::umma_f16_ts_w(tO, tPh + ac, dVh + advV, idO, (j | ks) ? 1u : 0u);
+          tc::umma_f16_ts_w(tO, tPh + ac, dVl + advV, idO, 1u);
+          tc::umma_f16_ts_w(tO, tPl + ac, dVh + advV, idO, 1u);
         }
-        tc::umma_commit(&o_full[q]);
+        tc::umma_commit_w(&o_full[q]);
       };
       ok = tc::mbar_wait(&q_ready[0], 0) && ok;
       ok = tc::mbar_wait(&q_ready[1], 0) && ok;
       for (int j = 0; j < 2 && j < T; ++j) {
         ok = tc::mbar_wait(&k_full[j], 0) && ok;
+        __syncwarp();
         tc::fence_after_sync();
         issue_S(0, j);
         issue_S(1, j);
-        tc::umma_commit(&k_empty[j]);
+        tc::umma_commit_w(&k_empty[j]);
       }
+#ifdef B2_ATTN_TIMING
+      const bool stamp = args.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+      AS_T0();
       for (int i = 0; i < T; ++i) {
         const int j2 = i + 2;
         const bool more = j2 < T;
         ok = tc::mbar_wait(&v_full[i % AS_NV], (i / AS_NV) & 1) && ok;
         if (more) ok = tc::mbar_wait(&k_full[j2 % AS_NK], (j2 / AS_NK) & 1) && ok;
+        AS_ACC(0);
         for (int q = 0; q < 2; ++q) {
           ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) stored over S_q(i); O_q rescaled if it had to be
+          __syncwarp();
           tc::fence_after_sync();
+          AS_ACC(1 + 2 * q);
           issue_PV(q, i);
           if (more) issue_S(q, j2);  // overwrites buffer i & 1 = P_q(i): in issue order after PV_q(i) has read it
+          AS_ACC(2 + 2 * q);
         }
-        tc::umma_commit(&v_empty[i % AS_NV]);
-        if (more) tc::umma_commit(&k_empty[j2 % AS_NK]);
+        tc::umma_commit_w(&v_empty[i % AS_NV]);
+        if (more) tc::umma_commit_w(&k_empty[j2 % AS_NK]);
       }
+#ifdef B2_ATTN_TIMING
+      if (stamp) for (int i = 0; i < 8; ++i) args.timing[16 + i] = tacc[i];
+#endif
     }
   } else {
     // ===== softmax warpgroups: q = 0 (warps 0-3), q = 1 (warps 4-7); thread = query row = TMEM lane =====
@@ -212,9 +236,15 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
       tc::mbar_arrive(&q_ready[q]);
     }
 
+#ifdef B2_ATTN_TIMING
+    const bool stamp = args.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (r == 0);
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    AS_T0();
     for (int i = 0; i < T; ++i) {
       ok = tc::mbar_wait(&s_full[q * 2 + (i & 1)], (i >> 1) & 1) && ok;
       tc::fence_after_sync();
+      AS_ACC(0);
       const uint32_t tS = tB + (i & 1) * 64;
       const int k0 = (tile0 + i) * AW_KV;
       float a[64];
@@ -229,6 +259,7 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
       for (int j = 1; j < 64; ++j) mx = fmaxf(mx, a[j]);
       const float m_new = fmaxf(m_ref, mx * c2);
       bool waited = false;
+      AS_ACC(1);
       if (__any_sync(0xffffffffu, m_new - m_ref > AS_RESCALE)) {  // also true on the first tile (m_ref = -inf)
         const float corr = tc::ex2(m_ref - m_new);
         l_i *= corr;
@@ -245,6 +276,7 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         }
         m_ref = m_new;
       }
+      AS_ACC(2);
       uint32_t ph[32], pl[32];
       float rs = 0.f;
 #pragma unroll
@@ -255,13 +287,21 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         tc::split2_unscaled(pa, pb, ph[jj], pl[jj]);
       }
       l_i += rs;
+      AS_ACC(3);
       tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
       tc::tmem_st32(tS + 32, pl);
       tc::tmem_st_wait();
+      AS_ACC(4);
       if (i > 0 && !waited) ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;  // consume every phase: keeps parities unambiguous
+      AS_ACC(5);
       tc::fence_before_sync();
       tc::mbar_arrive(&p_full[q]);
+      AS_ACC(6);
     }
+#ifdef B2_ATTN_TIMING
+    if (stamp) for (int i = 0; i < 8; ++i) args.timing[q * 8 + i] = tacc[i];
+    if (stamp) args.timing[24] = T;
+#endif
 #pragma unroll
     for (int j = 0; j < 64; ++j) o[j] = 0.f;
     if (T > 0) {

@@ -87,11 +87,12 @@ static __global__ void __launch_bounds__(128, 2) k_conv_tma(const __grid_constan
       tc::tma_load_2d(sB, &maps.wh, &full[s], kc * 64, n0);
       tc::tma_load_2d(sB + CV_B_BYTES, &maps.wl, &full[s], kc * 64, n0);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {  // whole warp, one elected lane issues (tc.cuh: warp-uniform issue)
     const uint32_t idesc = tc::idesc_f16(128, CV_N);
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % CV_STAGES;
       ok = tc::mbar_wait(&full[s], (kc / CV_STAGES) & 1) && ok;
+      __syncwarp();
       tc::fence_after_sync();
       const uint32_t aH = smem0 + s * CV_STAGE_BYTES, aL = aH + CV_A_BYTES, bH = aH + 2 * CV_A_BYTES, bL = bH + CV_B_BYTES;
       const uint64_t dAh = tc::smem_desc_sw128(aH), dAl = tc::smem_desc_sw128(aL), dBh = tc::smem_desc_sw128(bH), dBl = tc::smem_desc_sw128(bL);
@@ -99,13 +100,13 @@ static __global__ void __launch_bounds__(128, 2) k_conv_tma(const __grid_constan
       for (int ks = 0; ks < 4; ++ks) {
         const uint64_t adv = (uint64_t)(ks * 2);
         const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-        tc::umma_f16(tmem, dAh + adv, dBh + adv, idesc, first);
-        tc::umma_f16(tmem + CV_N, dAh + adv, dBl + adv, idesc, first);
-        tc::umma_f16(tmem + CV_N, dAl + adv, dBh + adv, idesc, 1u);
+        tc::umma_f16_w(tmem, dAh + adv, dBh + adv, idesc, first);
+        tc::umma_f16_w(tmem + CV_N, dAh + adv, dBl + adv, idesc, first);
+        tc::umma_f16_w(tmem + CV_N, dAl + adv, dBh + adv, idesc, 1u);
       }
-      tc::umma_commit(&empty[s]);
+      tc::umma_commit_w(&empty[s]);
     }
-    tc::umma_commit(accum);
+    tc::umma_commit_w(accum);
   }
   __syncwarp();
   ok = tc::mbar_wait(accum, 0) && ok;

@@ -116,12 +116,13 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tma(const __grid_constan
       tc::tma_load_2d(sB, &maps.bh, &full[s], k0, n0);
       tc::tma_load_2d(sB + TM_B_BYTES, &maps.bl, &full[s], k0, n0);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the loop with uniform operands, one elected lane issues (tc.cuh) =====
     const uint32_t idesc = tc::idesc_f16(TM_M, TM_N);
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % TM_STAGES;
       ok = tc::mbar_wait(&full[s], (kc / TM_STAGES) & 1) && ok;
+      __syncwarp();
       tc::fence_after_sync();
       const uint32_t aH = smem0 + s * TM_STAGE_BYTES, aL = aH + TM_A_BYTES, bH = aH + 2 * TM_A_BYTES, bL = bH + TM_B_BYTES;
       const uint64_t dAh = tc::smem_desc_sw128(aH), dAl = tc::smem_desc_sw128(aL), dBh = tc::smem_desc_sw128(bH), dBl = tc::smem_desc_sw128(bL);
@@ -129,13 +130,13 @@ static __global__ void __launch_bounds__(128, 2) k_gemm_tma(const __grid_constan
       for (int ks = 0; ks < TM_K / 16; ++ks) {
         const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the start-address field
         const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-        tc::umma_f16(tmem, dAh + adv, dBh + adv, idesc, first);         // acc0 (+)= Ah Bh
-        tc::umma_f16(tmem + TM_N, dAh + adv, dBl + adv, idesc, first);  // acc1 (+)= Ah Bl
-        tc::umma_f16(tmem + TM_N, dAl + adv, dBh + adv, idesc, 1u);     // acc1  += Al Bh
+        tc::umma_f16_w(tmem, dAh + adv, dBh + adv, idesc, first);         // acc0 (+)= Ah Bh
+        tc::umma_f16_w(tmem + TM_N, dAh + adv, dBl + adv, idesc, first);  // acc1 (+)= Ah Bl
+        tc::umma_f16_w(tmem + TM_N, dAl + adv, dBh + adv, idesc, 1u);     // acc1  += Al Bh
       }
-      tc::umma_commit(&empty[s]);
+      tc::umma_commit_w(&empty[s]);
     }
-    tc::umma_commit(accum);
+    tc::umma_commit_w(accum);
   }
   __syncwarp();
   ok = tc::mbar_wait(accum, 0) && ok;
