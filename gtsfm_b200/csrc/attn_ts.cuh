@@ -15,7 +15,10 @@
 //     [128,192) O accumulator (128 x 64 fp32), accumulated by the tensor core across ALL key tiles
 //     [192,224) Q hi, [224,256) Q lo  (column c = dims 2c, 2c + 1)
 //   warp 8 lane 0 : TMA producer - K and V tiles through two 4-stage rings (128-byte swizzled, zero OOB fill)
-//   warp 9        : TMEM allocator + MMA issuer (warp-uniform, one elected lane).  Per key tile i and query tile q, in the order
+//   warps 9, 10   : MMA issuers of query tile 0 / 1 (warp-uniform issue, one elected lane; warp 9 also owns the TMEM
+//                   allocation).  Two issuers because a barrier wait costs the issuing warp 150-250 cycles and the
+//                   tcgen05 queue is shallow: while one warp waits for its P tile the other's MMAs keep the pipe busy.
+//                   Per key tile i, issuer q:
 //                     PV_q(i): O_q += Ph Vh + Ph Vl + Pl Vh   (A = P from TMEM, B = V MN-major)      12 tcgen05.mma
 //                     S_q(i+2) = Qh Kh^T + Qh Kl^T + Ql Kh^T  (A = Q from TMEM) into buffer i & 1    12 tcgen05.mma
 //                   the logits run two key tiles ahead of the softmax.
@@ -29,12 +32,13 @@
 #pragma once
 #include "attn_ws.cuh"
 
-constexpr int AS_NK = 4, AS_NV = 4;                       // ring depths
-constexpr int AS_STAGE = 2 * AW_KV_BYTES;                 // hi + lo plane of one 64 x 64 tile = 16 KB
-constexpr int AS_OFF_K = 0, AS_OFF_V = AS_NK * AS_STAGE;  // 64 KB each
-constexpr int AS_TILE_BYTES = AS_OFF_V + AS_NV * AS_STAGE;
+constexpr int AS_NS = 4;                     // ring depth; entry e holds K tile e and V tile e - 2 (consumed together)
+constexpr int AS_HALF = 2 * AW_KV_BYTES;     // hi + lo plane of one 64 x 64 tile = 16 KB
+constexpr int AS_STAGE = 2 * AS_HALF;        // K part at +0, V part at +AS_HALF
+constexpr int AS_TILE_BYTES = AS_NS * AS_STAGE;
 constexpr size_t AS_SMEM = AS_TILE_BYTES + 1024 + 512;
 constexpr uint32_t AS_COL_O = 128, AS_COL_Q = 192;
+constexpr int AS_THREADS = 352;     // 8 softmax warps + TMA producer warp + 2 MMA issuer warps
 constexpr float AS_RESCALE = 8.0f;  // log2 of the largest P allowed before the reference maximum is refreshed
 
 struct AttnTsMaps {
@@ -65,17 +69,15 @@ struct AttnTsArgs {
 #define AS_ACC(slot) do { } while (0)
 #endif
 
-static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_constant__ AttnTsMaps maps, AttnTsArgs args) {
+static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ts(const __grid_constant__ AttnTsMaps maps, AttnTsArgs args) {
   extern __shared__ unsigned char as_raw[];
   const uint32_t raw = tc::smem_u32(as_raw);
   const uint32_t smem0 = (raw + 1023u) & ~1023u;
   unsigned char* sm = as_raw + (smem0 - raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AS_TILE_BYTES);
-  uint64_t* k_full = bars;                  // [AS_NK]
-  uint64_t* k_empty = k_full + AS_NK;       // [AS_NK]
-  uint64_t* v_full = k_empty + AS_NK;       // [AS_NV]
-  uint64_t* v_empty = v_full + AS_NV;       // [AS_NV]
-  uint64_t* s_full = v_empty + AS_NV;       // [4] query tile x logits buffer
+  uint64_t* kv_full = bars;                 // [AS_NS]
+  uint64_t* kv_empty = kv_full + AS_NS;     // [AS_NS]
+  uint64_t* s_full = kv_empty + AS_NS;      // [4] query tile x logits buffer
   uint64_t* p_full = s_full + 4;            // [2]
   uint64_t* o_full = p_full + 2;            // [2]
   uint64_t* q_ready = o_full + 2;           // [2]
@@ -93,8 +95,7 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
   const int T = tile1 - tile0;  // may be <= 0 for a trailing split: then this CTA writes neutral partials
 
   if (t == 0) {
-    for (int i = 0; i < AS_NK; ++i) tc::mbar_init(&k_full[i], 1), tc::mbar_init(&k_empty[i], 1);
-    for (int i = 0; i < AS_NV; ++i) tc::mbar_init(&v_full[i], 1), tc::mbar_init(&v_empty[i], 1);
+    for (int i = 0; i < AS_NS; ++i) tc::mbar_init(&kv_full[i], 1), tc::mbar_init(&kv_empty[i], 2);  // released by both issuers
     for (int i = 0; i < 4; ++i) tc::mbar_init(&s_full[i], 1);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&p_full[i], 128), tc::mbar_init(&o_full[i], 1), tc::mbar_init(&q_ready[i], 128);
     tc::fence_mbar_init();
@@ -108,39 +109,35 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
 
   if (warp == 8) {
     if (lane == 0 && T > 0) {
-      // ===== TMA producer: K(0), K(1), then V(i), K(i+2) in the order the issuer consumes them =====
-      auto load_k = [&](int j) {
-        const int s = j % AS_NK;
-        if (j >= AS_NK) ok = tc::mbar_wait(&k_empty[s], ((j / AS_NK) - 1) & 1) && ok;
-        tc::mbar_expect_tx(&k_full[s], AS_STAGE);
-        const int row = h * Nk + (tile0 + j) * AW_KV;
-        tc::tma_load_2d(smem0 + AS_OFF_K + s * AS_STAGE, &maps.kh[z], &k_full[s], 0, row);
-        tc::tma_load_2d(smem0 + AS_OFF_K + s * AS_STAGE + AW_KV_BYTES, &maps.kl[z], &k_full[s], 0, row);
-      };
-      auto load_v = [&](int j) {
-        const int s = j % AS_NV;
-        if (j >= AS_NV) ok = tc::mbar_wait(&v_empty[s], ((j / AS_NV) - 1) & 1) && ok;
-        tc::mbar_expect_tx(&v_full[s], AS_STAGE);
-        const int row = h * Nk + (tile0 + j) * AW_KV;
-        tc::tma_load_2d(smem0 + AS_OFF_V + s * AS_STAGE, &maps.vh[z], &v_full[s], 0, row);
-        tc::tma_load_2d(smem0 + AS_OFF_V + s * AS_STAGE + AW_KV_BYTES, &maps.vl[z], &v_full[s], 0, row);
-      };
-      load_k(0);
-      if (T > 1) load_k(1);
-      for (int i = 0; i < T; ++i) {
-        load_v(i);
-        if (i + 2 < T) load_k(i + 2);
+      // ===== TMA producer: ring entry e = K tile e (if any) + V tile e - 2 (if any), one barrier pair per entry =====
+      for (int e = 0; e < T + 2; ++e) {
+        const int s = e % AS_NS;
+        if (e >= AS_NS) ok = tc::mbar_wait(&kv_empty[s], ((e / AS_NS) - 1) & 1) && ok;
+        const bool hk = e < T, hv = e >= 2;
+        tc::mbar_expect_tx(&kv_full[s], (hk ? AS_HALF : 0) + (hv ? AS_HALF : 0));
+        const uint32_t dst = smem0 + s * AS_STAGE;
+        if (hk) {
+          const int row = h * Nk + (tile0 + e) * AW_KV;
+          tc::tma_load_2d(dst, &maps.kh[z], &kv_full[s], 0, row);
+          tc::tma_load_2d(dst + AW_KV_BYTES, &maps.kl[z], &kv_full[s], 0, row);
+        }
+        if (hv) {
+          const int row = h * Nk + (tile0 + e - 2) * AW_KV;
+          tc::tma_load_2d(dst + AS_HALF, &maps.vh[z], &kv_full[s], 0, row);
+          tc::tma_load_2d(dst + AS_HALF + AW_KV_BYTES, &maps.vl[z], &kv_full[s], 0, row);
+        }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp >= 9) {
     if (T > 0) {
+      const int q = warp - 9;  // each issuer warp owns one query tile: its barrier waits overlap the other's MMAs
       // ===== MMA issuer: the whole warp runs this with uniform operands, one elected lane issues (tc.cuh) =====
       const uint32_t idS = tc::idesc_f16(AW_Q, AW_KV);                        // Q K^T: A (TMEM) and B K-major
       const uint32_t idO = tc::idesc_f16(AW_Q, AW_D) | tc::IDESC_B_MN_MAJOR;  // P V: V as stored = MN-major
       auto issue_S = [&](int q, int j) {  // logits of key tile j into buffer j & 1
-        const int s = j % AS_NK;
-        const uint64_t dKh = tc::smem_desc_sw128(smem0 + AS_OFF_K + s * AS_STAGE);
-        const uint64_t dKl = tc::smem_desc_sw128(smem0 + AS_OFF_K + s * AS_STAGE + AW_KV_BYTES);
+        const int s = j % AS_NS;  // ring entry j
+        const uint64_t dKh = tc::smem_desc_sw128(smem0 + s * AS_STAGE);
+        const uint64_t dKl = tc::smem_desc_sw128(smem0 + s * AS_STAGE + AW_KV_BYTES);
         const uint32_t tS = tmem + q * 256 + (j & 1) * 64;
         const uint32_t tQh = tmem + q * 256 + AS_COL_Q, tQl = tQh + 32;
 #pragma unroll
@@ -154,9 +151,9 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         tc::umma_commit_w(&s_full[q * 2 + (j & 1)]);
       };
       auto issue_PV = [&](int q, int j) {
-        const int s = j % AS_NV;
-        const uint64_t dVh = tc::smem_desc_sw128_mn(smem0 + AS_OFF_V + s * AS_STAGE);
-        const uint64_t dVl = tc::smem_desc_sw128_mn(smem0 + AS_OFF_V + s * AS_STAGE + AW_KV_BYTES);
+        const int s = (j + 2) % AS_NS;  // ring entry j + 2
+        const uint64_t dVh = tc::smem_desc_sw128_mn(smem0 + s * AS_STAGE + AS_HALF);
+        const uint64_t dVl = tc::smem_desc_sw128_mn(smem0 + s * AS_STAGE + AS_HALF + AW_KV_BYTES);
         const uint32_t tPh = tmem + q * 256 + (j & 1) * 64, tPl = tPh + 32;
         const uint32_t tO = tmem + q * 256 + AS_COL_O;
 #pragma unroll
@@ -169,41 +166,37 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
         }
         tc::umma_commit_w(&o_full[q]);
       };
-      ok = tc::mbar_wait(&q_ready[0], 0) && ok;
-      ok = tc::mbar_wait(&q_ready[1], 0) && ok;
+      ok = tc::mbar_wait(&q_ready[q], 0) && ok;
       for (int j = 0; j < 2 && j < T; ++j) {
-        ok = tc::mbar_wait(&k_full[j], 0) && ok;
+        ok = tc::mbar_wait(&kv_full[j], 0) && ok;
         __syncwarp();
         tc::fence_after_sync();
-        issue_S(0, j);
-        issue_S(1, j);
-        tc::umma_commit_w(&k_empty[j]);
+        issue_S(q, j);
+        tc::umma_commit_w(&kv_empty[j]);
       }
 #ifdef B2_ATTN_TIMING
       const bool stamp = args.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
       long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
       AS_T0();
+      bool h_kv = false;  // ring entry already seen complete by a pre-poll issued before the previous batch of MMAs
       for (int i = 0; i < T; ++i) {
-        const int j2 = i + 2;
-        const bool more = j2 < T;
-        ok = tc::mbar_wait(&v_full[i % AS_NV], (i / AS_NV) & 1) && ok;
-        if (more) ok = tc::mbar_wait(&k_full[j2 % AS_NK], (j2 / AS_NK) & 1) && ok;
+        const int e = i + 2;  // ring entry: V tile i and (if any) K tile i + 2
+        const bool more = e < T;
+        if (!h_kv) ok = tc::mbar_wait(&kv_full[e % AS_NS], (e / AS_NS) & 1) && ok;
         AS_ACC(0);
-        for (int q = 0; q < 2; ++q) {
-          ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) stored over S_q(i); O_q rescaled if it had to be
-          __syncwarp();
-          tc::fence_after_sync();
-          AS_ACC(1 + 2 * q);
-          issue_PV(q, i);
-          if (more) issue_S(q, j2);  // overwrites buffer i & 1 = P_q(i): in issue order after PV_q(i) has read it
-          AS_ACC(2 + 2 * q);
-        }
-        tc::umma_commit_w(&v_empty[i % AS_NV]);
-        if (more) tc::umma_commit_w(&k_empty[j2 % AS_NK]);
+        ok = tc::mbar_wait(&p_full[q], i & 1) && ok;  // P_q(i) stored over S_q(i); O_q rescaled if it had to be
+        __syncwarp();
+        tc::fence_after_sync();
+        AS_ACC(1);
+        h_kv = (i + 1 < T) && tc::mbar_test(&kv_full[(e + 1) % AS_NS], ((e + 1) / AS_NS) & 1);
+        issue_PV(q, i);
+        if (more) issue_S(q, e);  // overwrites buffer i & 1 = P_q(i): in issue order after PV_q(i) has read it
+        tc::umma_commit_w(&kv_empty[e % AS_NS]);
+        AS_ACC(2);
       }
 #ifdef B2_ATTN_TIMING
-      if (stamp) for (int i = 0; i < 8; ++i) args.timing[16 + i] = tacc[i];
+      if (stamp) for (int i = 0; i < 3; ++i) args.timing[16 + 3 * q + i] = tacc[i];
 #endif
     }
   } else {
@@ -241,8 +234,9 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     AS_T0();
+    bool h_s = false;  // pre-polled: logits of the next tile already complete
     for (int i = 0; i < T; ++i) {
-      ok = tc::mbar_wait(&s_full[q * 2 + (i & 1)], (i >> 1) & 1) && ok;
+      if (!h_s) ok = tc::mbar_wait(&s_full[q * 2 + (i & 1)], (i >> 1) & 1) && ok;
       tc::fence_after_sync();
       AS_ACC(0);
       const uint32_t tS = tB + (i & 1) * 64;
@@ -258,13 +252,13 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
 #pragma unroll
       for (int j = 1; j < 64; ++j) mx = fmaxf(mx, a[j]);
       const float m_new = fmaxf(m_ref, mx * c2);
-      bool waited = false;
+      bool waited = i == 0 || tc::mbar_test(&o_full[q], (i - 1) & 1);  // PV_q(i-1) landed? (pre-poll, consumed below)
       AS_ACC(1);
       if (__any_sync(0xffffffffu, m_new - m_ref > AS_RESCALE)) {  // also true on the first tile (m_ref = -inf)
         const float corr = tc::ex2(m_ref - m_new);
         l_i *= corr;
         if (i > 0) {  // bring O (in TMEM) to the new reference; PV_q(i-1) must have landed
-          ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;
+          if (!waited) ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;
           tc::fence_after_sync();
           waited = true;
           tc::tmem_ld64(tO, o);
@@ -288,11 +282,12 @@ static __global__ void __launch_bounds__(AW_THREADS, 1) k_flash_ts(const __grid_
       }
       l_i += rs;
       AS_ACC(3);
+      h_s = (i + 1 < T) && tc::mbar_test(&s_full[q * 2 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
       tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
       tc::tmem_st32(tS + 32, pl);
       tc::tmem_st_wait();
       AS_ACC(4);
-      if (i > 0 && !waited) ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;  // consume every phase: keeps parities unambiguous
+      if (!waited) ok = tc::mbar_wait(&o_full[q], (i - 1) & 1) && ok;  // every phase is observed once: parities stay unambiguous
       AS_ACC(5);
       tc::fence_before_sync();
       tc::mbar_arrive(&p_full[q]);

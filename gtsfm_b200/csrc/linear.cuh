@@ -210,7 +210,7 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     const double flops = 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk);
     if (ts) {
       b2_prof_work(ctx, "k_flash_ts", flops);
-      B2_LAUNCH(ctx, k_flash_ts, dim3(qt, 4, 2 * nsplit), AW_THREADS, AS_SMEM, st, tmaps, ta);
+      B2_LAUNCH(ctx, k_flash_ts, dim3(qt, 4, 2 * nsplit), AS_THREADS, AS_SMEM, st, tmaps, ta);
     } else {
       b2_prof_work(ctx, "k_flash_ws", flops);
       B2_LAUNCH(ctx, k_flash_ws, dim3(qt, 4, 2 * nsplit), AW_THREADS, AW_SMEM, st, maps, wa);

@@ -37,6 +37,21 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+// Non-blocking probe of a phase (mbarrier.test_wait).  Used to PRE-POLL a barrier while other work is being issued: a
+// blocking wait costs 150-250 cycles even when the phase completed long ago (measured, scratch/attn_bench.cu), which a
+// shallow tcgen05 queue turns straight into idle tensor cycles; `if (!hint) mbar_wait(...)` keeps correctness.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // ---- TMEM -------------------------------------------------------------------------------------------------------
 // one full warp; ncols power of two >= 32.  The allocated base address is written to *dst_smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

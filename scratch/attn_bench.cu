@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0), cudaEventCreate(&e1);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    k_flash_ts<<<dim3(qt, 4, 2 * nsplit), AW_THREADS, AS_SMEM>>>(maps, a);
+    k_flash_ts<<<dim3(qt, 4, 2 * nsplit), AS_THREADS, AS_SMEM>>>(maps, a);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms;
@@ -68,10 +68,10 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 7; ++i) printf(" %s %.0f |", wg[i], t[q * 8 + i] / T), s += t[q * 8 + i] / T;
     printf(" total %.0f\n", s);
   }
-  const char* mm[5] = {"wait kv", "wait p0", "issue0", "wait p1", "issue1"};
+  const char* mm[6] = {"A:wait kv", "wait p0", "issue0", "B:wait kv", "wait p1", "issue1"};
   double s = 0;
   printf(" MMA:");
-  for (int i = 0; i < 5; ++i) printf(" %s %.0f |", mm[i], t[16 + i] / T), s += t[16 + i] / T;
+  for (int i = 0; i < 6; ++i) printf(" %s %.0f |", mm[i], t[16 + i] / T), s += t[16 + i] / T;
   printf(" total %.0f\n", s);
   return 0;
 }
