@@ -48,9 +48,6 @@ struct AttnWsArgs {
 };
 
 namespace tc {
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // MN-major operand stored [k][64 mn-elements] with 128-byte rows, 128-byte swizzle: SBO = 8-row group stride
 __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr) { return smem_desc_sw128(saddr); }
 }  // namespace tc

@@ -6,6 +6,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
+#include "gemm_ws.cuh"
 #include "attn_ws.cuh"
 #include "attn_ts.cuh"
 #include <cstdlib>
@@ -32,6 +33,14 @@ static inline bool attn_use_ts() {
     return !(e && e[0] == '1');
   }();
   return ts;
+}
+// persistent warp-specialised GEMM (k_gemm_ws, default); B2_GEMM_WS=0 selects the one-tile-per-CTA k_gemm_tma
+static inline bool gemm_use_ws() {
+  static const bool ws = [] {
+    const char* e = getenv("B2_GEMM_WS");
+    return !(e && e[0] == '0');
+  }();
+  return ws;
 }
 static inline bool attn_v_unscaled(const TcWeights& tw) { return attn_qk_unscaled(tw) && attn_use_ts(); }
 
@@ -118,6 +127,17 @@ static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     q.K1 = a.K1, q.K2 = a.K2, q.N = a.N, q.bias = a.bias, q.ldr = a.ldr, q.scale = a.scale, q.ldc = a.ldc, q.ldch = a.ldch;
     q.head_major = a.head_major, q.relu = a.relu, q.lo_unscaled = a.lo_unscaled, q.err_flag = tw.err;
+    if (gemm_use_ws()) {  // persistent, epilogue overlapped with the next tile's MMAs
+      GemmWsArgs wq{};
+      wq.g = q;
+      wq.tiles_n = cdiv(a.N, TM_N), wq.tiles_m0 = cdiv(a.M, TM_M);
+      wq.tiles = wq.tiles_n * (wq.tiles_m0 + (b ? cdiv(b->M, TM_M) : 0));
+      if (wq.tiles <= 0) return B2_OK;
+      b2_prof_work(ctx, "k_gemm_ws", work);
+      B2_LAUNCH(ctx, k_gemm_ws, wq.tiles < tw.sm_count ? wq.tiles : tw.sm_count, GW_THREADS, GW_SMEM, st, maps, wq);
+      B2_CHECK_LAUNCH(ctx);
+      return B2_OK;
+    }
     dim3 grid(cdiv(a.N, TM_N), cdiv(maxM, TM_M), b ? 2 : 1);
     b2_prof_work(ctx, "k_gemm_tma", work);
     B2_LAUNCH(ctx, k_gemm_tma, grid, 128, TM_GEMM_SMEM, st, maps, q);
