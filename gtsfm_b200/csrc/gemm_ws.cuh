@@ -13,7 +13,7 @@
 #pragma once
 #include "gemm_tma.cuh"
 
-constexpr int GW_STAGES = 3;
+constexpr int GW_STAGES = 4;
 constexpr int GW_THREADS = 320;
 constexpr int GW_SCRATCH = 8 * 32 * 33 * 4;  // one 32 x 33 fp32 transpose pad per epilogue warp
 constexpr size_t GW_SMEM = GW_STAGES * TM_STAGE_BYTES + GW_SCRATCH + 1024 /*align slack*/ + 256 /*barriers*/;
