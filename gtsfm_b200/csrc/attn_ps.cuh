@@ -1,0 +1,350 @@
+// Persistent schedule of the TMEM-operand flash attention (attn_ts.cuh): same per-tile pipeline, different work split.
+//
+// k_flash_ts launches (query-tile pair, head, problem, key split) CTAs: 640 CTAs of 20 key tiles each on 148 SMs = 4.3
+// waves with ~30 % of every CTA's life spent in prologue / epilogue (TMEM alloc, Q load, pipeline fill, partial store).
+// Here the whole launch is ONE linear space of (item, key tile) units - item = (problem, head, 256-query block) - cut
+// into equal contiguous ranges, one per SM ("stream-K" over the key dimension).  A CTA therefore runs 1-3 SEGMENTS
+// (item, key-tile range) back to back: TMEM stays allocated, the barriers keep running phase counters, the TMA producer
+// streams the next segment's K / V tiles while the current one drains, and the next segment's Q is stored and its first
+// logits issued before the softmax warps write the current segment's result.  A segment that covers its item completely
+// writes the normalised output planes; otherwise it writes an un-normalised partial (O, m, l) that k_attn_merge_ps
+// combines (<= 2-3 partials per item instead of 4).
+//
+// TMEM layout, warp roles and hand-offs are those of attn_ts.cuh; all barrier parities are functions of running counters
+// (ring entry `ge`, tile `gt`, segment `seg`) that every role advances identically.
+#pragma once
+#include "attn_ts.cuh"
+
+struct AttnPsProblem {
+  const __half *Qh, *Ql;  // head-major planes [4][Nq][64]
+  __half *Oh, *Ol;        // final output planes [Nq][256]
+  int Nq, Nk;
+  int qt, tiles;          // 256-query blocks, 64-key tiles
+};
+struct AttnPsArgs {
+  AttnPsProblem p[2];
+  float* Opart;  // [item][max_splits][256][64] fp32, un-normalised
+  float* ml;     // [item][max_splits][256][2]
+  int W0, W;     // units of problem 0, total units
+  int quota;     // units per CTA
+  int max_splits;
+  float scale;
+  int* err_flag;
+};
+
+struct AttnPsSeg {
+  int z, item, h, q0, tile0, T, split, nsplits, itemg;
+};
+// segment starting at unit w (clipped to w_end)
+__device__ __forceinline__ AttnPsSeg attn_ps_decode(const AttnPsArgs& a, int w, int w_end) {
+  AttnPsSeg s;
+  s.z = w >= a.W0 ? 1 : 0;
+  const AttnPsProblem& p = a.p[s.z];
+  const int base = s.z ? a.W0 : 0;
+  const int wl = w - base;
+  s.item = wl / p.tiles;
+  s.tile0 = wl - s.item * p.tiles;
+  s.T = min(p.tiles - s.tile0, w_end - w);
+  s.h = s.item / p.qt;
+  s.q0 = (s.item - s.h * p.qt) * (2 * AW_Q);
+  const int wi0 = base + s.item * p.tiles, wi1 = wi0 + p.tiles;
+  const int c_first = wi0 / a.quota;
+  s.split = w / a.quota - c_first;
+  s.nsplits = (wi1 - 1) / a.quota - c_first + 1;
+  s.itemg = (s.z ? a.p[0].qt * 4 : 0) + s.item;
+  return s;
+}
+
+static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_constant__ AttnTsMaps maps, AttnPsArgs args) {
+  extern __shared__ unsigned char ap_raw[];
+  const uint32_t raw = tc::smem_u32(ap_raw);
+  const uint32_t smem0 = (raw + 1023u) & ~1023u;
+  unsigned char* sm = ap_raw + (smem0 - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AS_TILE_BYTES);
+  uint64_t* kv_full = bars;                 // [AS_NS]
+  uint64_t* kv_empty = kv_full + AS_NS;     // [AS_NS]
+  uint64_t* s_full = kv_empty + AS_NS;      // [4] query tile x logits buffer
+  uint64_t* p_full = s_full + 4;            // [2]
+  uint64_t* o_full = p_full + 2;            // [2]
+  uint64_t* q_ready = o_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 2);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int w_begin = blockIdx.x * args.quota;
+  const int w_end = min(args.W, w_begin + args.quota);
+
+  if (t == 0) {
+    for (int i = 0; i < AS_NS; ++i) tc::mbar_init(&kv_full[i], 1), tc::mbar_init(&kv_empty[i], 2);  // released by both issuers
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&p_full[i], 128), tc::mbar_init(&o_full[i], 1), tc::mbar_init(&q_ready[i], 128);
+    tc::fence_mbar_init();
+  }
+  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  bool ok = true;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ===== TMA producer: ring entry e of a segment = K tile e (if any) + V tile e - 2 (if any) =====
+      int ge = 0;
+      for (int w = w_begin; w < w_end;) {
+        const AttnPsSeg sg = attn_ps_decode(args, w, w_end);
+        const int Nk = args.p[sg.z].Nk;
+        for (int e = 0; e < sg.T + 2; ++e) {
+          const int g = ge + e, s = g % AS_NS;
+          if (g >= AS_NS) ok = tc::mbar_wait(&kv_empty[s], ((g / AS_NS) - 1) & 1) && ok;
+          const bool hk = e < sg.T, hv = e >= 2;
+          tc::mbar_expect_tx(&kv_full[s], (hk ? AS_HALF : 0) + (hv ? AS_HALF : 0));
+          const uint32_t dst = smem0 + s * AS_STAGE;
+          if (hk) {
+            const int row = sg.h * Nk + (sg.tile0 + e) * AW_KV;
+            tc::tma_load_2d(dst, &maps.kh[sg.z], &kv_full[s], 0, row);
+            tc::tma_load_2d(dst + AW_KV_BYTES, &maps.kl[sg.z], &kv_full[s], 0, row);
+          }
+          if (hv) {
+            const int row = sg.h * Nk + (sg.tile0 + e - 2) * AW_KV;
+            tc::tma_load_2d(dst + AS_HALF, &maps.vh[sg.z], &kv_full[s], 0, row);
+            tc::tma_load_2d(dst + AS_HALF + AW_KV_BYTES, &maps.vl[sg.z], &kv_full[s], 0, row);
+          }
+        }
+        ge += sg.T + 2;
+        w += sg.T;
+      }
+    }
+  } else if (warp >= 9) {
+    // ===== MMA issuer of query tile q (whole warp, one elected lane issues) =====
+    const int q = warp - 9;
+    const uint32_t idS = tc::idesc_f16(AW_Q, AW_KV);                        // Q K^T: A (TMEM) and B K-major
+    const uint32_t idO = tc::idesc_f16(AW_Q, AW_D) | tc::IDESC_B_MN_MAJOR;  // P V: V as stored = MN-major
+    const uint32_t tQh = tmem + q * 256 + AS_COL_Q, tQl = tQh + 32;
+    const uint32_t tO = tmem + q * 256 + AS_COL_O;
+    int ge = 0, gt = 0, seg = 0;
+    for (int w = w_begin; w < w_end; ++seg) {
+      const AttnPsSeg sg = attn_ps_decode(args, w, w_end);
+      const int T = sg.T;
+      auto issue_S = [&](int j) {  // logits of the segment's key tile j: ring entry ge + j, logits buffer (gt + j) & 1
+        const int s = (ge + j) % AS_NS, buf = (gt + j) & 1;
+        const uint64_t dKh = tc::smem_desc_sw128(smem0 + s * AS_STAGE);
+        const uint64_t dKl = tc::smem_desc_sw128(smem0 + s * AS_STAGE + AW_KV_BYTES);
+        const uint32_t tS = tmem + q * 256 + buf * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);
+          const uint32_t ac = (uint32_t)(ks * 8);
+          tc::umma_f16_ts_w(tS, tQh + ac, dKh + adv, idS, ks ? 1u : 0u);
+          tc::umma_f16_ts_w(tS, tQh + ac, dKl + adv, idS, 1u);
+          tc::umma_f16_ts_w(tS, tQl + ac, dKh + adv, idS, 1u);
+        }
+        tc::umma_commit_w(&s_full[q * 2 + buf]);
+      };
+      auto issue_PV = [&](int j) {  // V tile j sits in ring entry ge + j + 2; P in logits buffer (gt + j) & 1
+        const int s = (ge + j + 2) % AS_NS, buf = (gt + j) & 1;
+        const uint64_t dVh = tc::smem_desc_sw128_mn(smem0 + s * AS_STAGE + AS_HALF);
+        const uint64_t dVl = tc::smem_desc_sw128_mn(smem0 + s * AS_STAGE + AS_HALF + AW_KV_BYTES);
+        const uint32_t tPh = tmem + q * 256 + buf * 64, tPl = tPh + 32;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ac = (uint32_t)(ks * 8);
+          const uint64_t advV = (uint64_t)(ks * 128);
+          tc::umma_f16_ts_w(tO, tPh + ac, dVh + advV, idO, (j | ks) ? 1u : 0u);
+          tc::umma_f16_ts_w(tO, tPh + ac, dVl + advV, idO, 1u);
+          tc::umma_f16_ts_w(tO, tPl + ac, dVh + advV, idO, 1u);
+        }
+        tc::umma_commit_w(&o_full[q]);
+      };
+      ok = tc::mbar_wait(&q_ready[q], seg & 1) && ok;  // this segment's Q rows are in TMEM
+      for (int j = 0; j < 2 && j < T; ++j) {
+        const int g = ge + j;
+        ok = tc::mbar_wait(&kv_full[g % AS_NS], (g / AS_NS) & 1) && ok;
+        __syncwarp();
+        tc::fence_after_sync();
+        issue_S(j);
+        tc::umma_commit_w(&kv_empty[g % AS_NS]);
+      }
+      if (T == 1) {  // ring entry 1 of a one-tile segment is empty but still cycles through the ring
+        const int g = ge + 1;
+        ok = tc::mbar_wait(&kv_full[g % AS_NS], (g / AS_NS) & 1) && ok;
+        __syncwarp();
+        tc::umma_commit_w(&kv_empty[g % AS_NS]);
+      }
+      bool h_kv = false;
+      for (int i = 0; i < T; ++i) {
+        const int g = ge + i + 2;  // ring entry: V tile i and (if any) K tile i + 2
+        const bool more = i + 2 < T;
+        if (!h_kv) ok = tc::mbar_wait(&kv_full[g % AS_NS], (g / AS_NS) & 1) && ok;
+        ok = tc::mbar_wait(&p_full[q], (gt + i) & 1) && ok;  // P_q(i) stored over S_q(i); O_q rescaled if it had to be
+        __syncwarp();
+        tc::fence_after_sync();
+        h_kv = (i + 1 < T) && tc::mbar_test(&kv_full[(g + 1) % AS_NS], ((g + 1) / AS_NS) & 1);
+        issue_PV(i);
+        if (more) issue_S(i + 2);  // overwrites buffer (gt + i) & 1 = P_q(i): in issue order after PV_q(i) has read it
+        tc::umma_commit_w(&kv_empty[g % AS_NS]);
+      }
+      ge += T + 2, gt += T;
+      w += T;
+    }
+  } else {
+    // ===== softmax warpgroups: q = 0 (warps 0-3), q = 1 (warps 4-7); thread = query row = TMEM lane =====
+    const int q = warp >> 2;
+    const int r = t & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tB = tmem + q * 256 + lane_off, tO = tB + AS_COL_O;
+    const float c2 = args.scale * 1.4426950408889634f;
+
+    auto store_q = [&](const AttnPsSeg& sg) {  // this thread's query row of segment sg -> TMEM (zero rows past the end)
+      const AttnPsProblem& pr = args.p[sg.z];
+      const int qrow = sg.q0 + q * AW_Q + r;
+      uint32_t wv[32];
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const __half* src = (pl ? pr.Ql : pr.Qh) + ((size_t)sg.h * pr.Nq + qrow) * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (qrow < pr.Nq) v = __ldg(reinterpret_cast<const uint4*>(src) + c);
+          wv[4 * c] = v.x, wv[4 * c + 1] = v.y, wv[4 * c + 2] = v.z, wv[4 * c + 3] = v.w;
+        }
+        tc::tmem_st32(tB + AS_COL_Q + pl * 32, wv);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&q_ready[q]);
+    };
+
+    int gt = 0;
+    if (w_begin < w_end) store_q(attn_ps_decode(args, w_begin, w_end));
+    for (int w = w_begin; w < w_end;) {
+      const AttnPsSeg sg = attn_ps_decode(args, w, w_end);
+      const AttnPsProblem& pr = args.p[sg.z];
+      const int T = sg.T, Nk = pr.Nk;
+      float m_ref = -INFINITY, l_i = 0.f;
+      bool h_s = false;  // pre-polled: logits of the next tile already complete
+      for (int i = 0; i < T; ++i) {
+        const int gi = gt + i;
+        if (!h_s) ok = tc::mbar_wait(&s_full[q * 2 + (gi & 1)], (gi >> 1) & 1) && ok;
+        tc::fence_after_sync();
+        const uint32_t tS = tB + (gi & 1) * 64;
+        const int k0 = (sg.tile0 + i) * AW_KV;
+        float a[64];
+        tc::tmem_ld64(tS, a);
+        if (k0 + AW_KV > Nk) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (k0 + j >= Nk) a[j] = -INFINITY;  // 2^(-inf) = 0
+        }
+        float mx = a[0];
+#pragma unroll
+        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, a[j]);
+        const float m_new = fmaxf(m_ref, mx * c2);
+        // PV_q(i-1) landed?  (pre-poll, consumed below; the previous segment's last phase was consumed by its epilogue)
+        bool waited = i == 0 || tc::mbar_test(&o_full[q], (gi - 1) & 1);
+        if (__any_sync(0xffffffffu, m_new - m_ref > AS_RESCALE)) {  // also true on the first tile (m_ref = -inf)
+          const float corr = tc::ex2(m_ref - m_new);
+          l_i *= corr;
+          if (i > 0) {  // bring O (in TMEM) to the new reference
+            if (!waited) ok = tc::mbar_wait(&o_full[q], (gi - 1) & 1) && ok;
+            tc::fence_after_sync();
+            waited = true;
+            float o[64];
+            tc::tmem_ld64(tO, o);
+            uint32_t ow[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) ow[j] = __float_as_uint(o[j] * corr);
+            tc::tmem_st32(tO, ow);
+            tc::tmem_st32(tO + 32, ow + 32);
+          }
+          m_ref = m_new;
+        }
+        uint32_t ph[32], pl[32];
+        float rs = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float pa = tc::ex2(fmaf(a[2 * jj], c2, -m_ref));
+          const float pb = tc::ex2(fmaf(a[2 * jj + 1], c2, -m_ref));
+          rs += pa + pb;
+          tc::split2_unscaled(pa, pb, ph[jj], pl[jj]);
+        }
+        l_i += rs;
+        h_s = (i + 1 < T) && tc::mbar_test(&s_full[q * 2 + ((gi + 1) & 1)], ((gi + 1) >> 1) & 1);
+        tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
+        tc::tmem_st32(tS + 32, pl);
+        tc::tmem_st_wait();
+        if (!waited) ok = tc::mbar_wait(&o_full[q], (gi - 1) & 1) && ok;  // every phase is observed once
+        tc::fence_before_sync();
+        tc::mbar_arrive(&p_full[q]);
+      }
+      gt += T;
+      w += T;
+      // next segment's Q goes in now (all logits of this segment have completed), so its first MMAs overlap our epilogue
+      if (w < w_end) store_q(attn_ps_decode(args, w, w_end));
+      // ---- this segment's result ----
+      float o[64];
+      ok = tc::mbar_wait(&o_full[q], (gt - 1) & 1) && ok;
+      tc::fence_after_sync();
+      tc::tmem_ld64(tO, o);
+      tc::fence_before_sync();  // our read of O is ordered before the next segment's first PV (gated by our p_full arrival)
+      const int qrow = sg.q0 + q * AW_Q + r;
+      if (qrow < pr.Nq) {
+        if (sg.nsplits == 1) {
+          const float inv = 1.0f / l_i;
+          uint4* dh = reinterpret_cast<uint4*>(pr.Oh + (size_t)qrow * 256 + sg.h * 64);
+          uint4* dl = reinterpret_cast<uint4*>(pr.Ol + (size_t)qrow * 256 + sg.h * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+            dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          const size_t slot = (size_t)sg.itemg * args.max_splits + sg.split;
+          float4* dst = reinterpret_cast<float4*>(args.Opart + (slot * 256 + q * AW_Q + r) * 64);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          float* ml = args.ml + (slot * 256 + q * AW_Q + r) * 2;
+          ml[0] = m_ref;
+          ml[1] = l_i;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (!ok && args.err_flag) *args.err_flag = 1;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+}
+
+// combine the partials of items that were cut across CTAs; one thread per (problem row, head, column pair)
+static __global__ void __launch_bounds__(256) k_attn_merge_ps(AttnPsArgs a, int z) {
+  const AttnPsProblem& p = a.p[z];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over Nq * 4 heads * 32 column pairs
+  if (idx >= p.Nq * 128) return;
+  const int cp = idx & 31, h = (idx >> 5) & 3, qrow = idx >> 7;
+  const int item = h * p.qt + qrow / (2 * AW_Q), rr = qrow % (2 * AW_Q);
+  const int wi0 = (z ? a.W0 : 0) + item * p.tiles, wi1 = wi0 + p.tiles;
+  const int c_first = wi0 / a.quota;
+  const int ns = (wi1 - 1) / a.quota - c_first + 1;
+  if (ns == 1) return;  // written in final form by the attention kernel
+  const size_t slot0 = (size_t)((z ? a.p[0].qt * 4 : 0) + item) * a.max_splits;
+  float m = -INFINITY;
+  for (int s = 0; s < ns; ++s) m = fmaxf(m, a.ml[((slot0 + s) * 256 + rr) * 2]);
+  float l = 0.f, x = 0.f, y = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    const float* q = a.ml + ((slot0 + s) * 256 + rr) * 2;
+    const float wgt = tc::ex2(q[0] - m);
+    l = fmaf(q[1], wgt, l);
+    const float2 v = *reinterpret_cast<const float2*>(a.Opart + ((slot0 + s) * 256 + rr) * 64 + 2 * cp);
+    x = fmaf(v.x, wgt, x);
+    y = fmaf(v.y, wgt, y);
+  }
+  const float inv = 1.0f / l;
+  uint32_t hi, lo;
+  tc::split2(x * inv, y * inv, hi, lo);
+  *reinterpret_cast<uint32_t*>(p.Oh + (size_t)qrow * 256 + h * 64 + 2 * cp) = hi;
+  *reinterpret_cast<uint32_t*>(p.Ol + (size_t)qrow * 256 + h * 64 + 2 * cp) = lo;
+}

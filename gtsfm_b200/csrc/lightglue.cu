@@ -33,7 +33,7 @@ struct ConfW {
 }  // namespace
 
 struct LgSide {  // per-image workspace
-  DevBuf x[2], xs[2], qkv, q, k, v, ctx, msg, h, hs, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, amax, aidx;
+  DevBuf x[2], xs[2], qkv, q, k, v, ctx, msg, h, hs, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, lsg, amax, aidx;
   int cur = 0;  // which of x / xs / cs / sn / ind is live
   int n = 0;
   int cap = 0;  // rows allocated; split-plane buffers keep their lo plane at +cap * width halves whatever n shrinks to
@@ -64,7 +64,7 @@ void lg_destroy(b2_context* ctx) {
   for (auto& sd : s->side) {
     DevBuf* bufs[] = {&sd.x[0], &sd.x[1], &sd.xs[0], &sd.xs[1], &sd.hs, &sd.qkv, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.cs[0], &sd.cs[1],
                       &sd.sn[0], &sd.sn[1], &sd.ind[0], &sd.ind[1], &sd.conf, &sd.mat, &sd.src, &sd.md, &sd.rmax,
-                      &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
+                      &sd.rlog, &sd.ls, &sd.lsg, &sd.amax, &sd.aidx};
     for (DevBuf* b : bufs) b->release();
   }
   s->sim.release();
@@ -297,8 +297,15 @@ __global__ void __launch_bounds__(256) k_lg_gather(const int* __restrict__ src, 
 }
 
 // log-softmax statistics of sim rows: max and log(sum(exp(x - max)))  (F.log_softmax, lightglue.py:271). warp per row.
+__device__ __forceinline__ float logsigmoid(float z) {  // F.logsigmoid: min(z, 0) - log1p(exp(-|z|))
+  return fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
+}
+
+// Row statistics of log_softmax(sim, dim 2) (:271): warp per row.  Also tabulates logsigmoid(z) of the row's
+// matchability logit so the arg-max passes do not re-evaluate it per matrix element.
 __global__ void __launch_bounds__(256) k_lg_row_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ rmax,
-                                                       float* __restrict__ rlog) {
+                                                       float* __restrict__ rlog, const float* __restrict__ z,
+                                                       float* __restrict__ lsg) {
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= m) return;
   const float* row = sim + (size_t)r * n;
@@ -308,24 +315,35 @@ __global__ void __launch_bounds__(256) k_lg_row_stats(const float* __restrict__ 
   float s = 0.f;
   for (int j = lane; j < n; j += 32) s += expf(row[j] - mx);
   s = warp_sum(s);
-  if (lane == 0) rmax[r] = mx, rlog[r] = logf(s);
+  if (lane == 0) rmax[r] = mx, rlog[r] = logf(s), lsg[r] = logsigmoid(z[r]);
 }
-// same along columns (log_softmax of sim^T, :272): a block owns 32 columns; its 8 warps stride over the rows (each row
-// access is one coalesced 128-byte line), keeping an online (max, sum) pair that is merged across warps at the end.
-__global__ void __launch_bounds__(256) k_lg_col_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ cmax,
-                                                       float* __restrict__ clog) {
-  __shared__ float sm[8][32], ss[8][32];
+// same along columns (log_softmax of sim^T, :272): a block owns 32 columns; its 32 warps stride over the rows (each row
+// access is one coalesced 128-byte line, four independent loads in flight per warp - the pass is load-latency bound),
+// keeping an online (max, sum) pair that is merged across warps at the end.
+constexpr int LG_COL_WARPS = 32, LG_COL_UNROLL = 4;
+__global__ void __launch_bounds__(1024) k_lg_col_stats(const float* __restrict__ sim, int m, int n, float* __restrict__ cmax,
+                                                        float* __restrict__ clog, const float* __restrict__ z,
+                                                        float* __restrict__ lsg) {
+  __shared__ float sm[LG_COL_WARPS][32], ss[LG_COL_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   float mx = -INFINITY, s = 0.f;
   if (j < n) {
-    for (int i = warp; i < m; i += 8) {
-      float x = sim[(size_t)i * n + j];
-      if (x > mx) {
-        s = s * expf(mx - x) + 1.0f;
-        mx = x;
-      } else {
-        s += expf(x - mx);
+    for (int i0 = warp; i0 < m; i0 += LG_COL_WARPS * LG_COL_UNROLL) {
+      float x[LG_COL_UNROLL];
+#pragma unroll
+      for (int u = 0; u < LG_COL_UNROLL; ++u) {
+        const int i = i0 + u * LG_COL_WARPS;
+        x[u] = i < m ? sim[(size_t)i * n + j] : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < LG_COL_UNROLL; ++u) {
+        if (x[u] > mx) {
+          s = s * expf(mx - x[u]) + 1.0f;
+          mx = x[u];
+        } else if (x[u] > -INFINITY) {
+          s += expf(x[u] - mx);
+        }
       }
     }
   }
@@ -333,34 +351,30 @@ __global__ void __launch_bounds__(256) k_lg_col_stats(const float* __restrict__ 
   __syncthreads();
   if (warp == 0 && j < n) {
     float M = sm[0][lane];
-    for (int w = 1; w < 8; ++w) M = fmaxf(M, sm[w][lane]);
+    for (int w = 1; w < LG_COL_WARPS; ++w) M = fmaxf(M, sm[w][lane]);
     float S = 0.f;
-    for (int w = 0; w < 8; ++w)
+    for (int w = 0; w < LG_COL_WARPS; ++w)
       if (ss[w][lane] > 0.f) S += ss[w][lane] * expf(sm[w][lane] - M);
-    cmax[j] = M, clog[j] = logf(S);
+    cmax[j] = M, clog[j] = logf(S), lsg[j] = logsigmoid(z[j]);
   }
 }
 
-__device__ __forceinline__ float logsigmoid(float z) {  // F.logsigmoid: min(z, 0) - log1p(exp(-|z|))
-  return fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
-}
-
 // scores[i][j] = (log_softmax_rows + log_softmax_cols) + (logsigmoid(z0_i) + logsigmoid(z1_j))  (:269-274);
-// row arg-max (first maximum) per i. warp per row.
+// row arg-max (first maximum) per i. warp per row.  l0 / l1 = the tabulated logsigmoid terms.
 __global__ void __launch_bounds__(256) k_lg_row_argmax(const float* __restrict__ sim, int m, int n,
                                                         const float* __restrict__ rmax, const float* __restrict__ rlog,
                                                         const float* __restrict__ cmax, const float* __restrict__ clog,
-                                                        const float* __restrict__ z0, const float* __restrict__ z1,
+                                                        const float* __restrict__ l0g, const float* __restrict__ l1g,
                                                         float* __restrict__ best, int* __restrict__ arg) {
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= m) return;
   const float* row = sim + (size_t)r * n;
-  const float rm = rmax[r], rl = rlog[r], l0 = logsigmoid(z0[r]);
+  const float rm = rmax[r], rl = rlog[r], l0 = l0g[r];
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   for (int j = lane; j < n; j += 32) {
     float x = row[j];
-    float sc = (((x - rm) - rl) + ((x - cmax[j]) - clog[j])) + (l0 + logsigmoid(z1[j]));
+    float sc = (((x - rm) - rl) + ((x - cmax[j]) - clog[j])) + (l0 + l1g[j]);
     if (sc > bv) bv = sc, bi = j;
   }
 #pragma unroll
@@ -371,29 +385,42 @@ __global__ void __launch_bounds__(256) k_lg_row_argmax(const float* __restrict__
   }
   if (lane == 0) best[r] = bv, arg[r] = bi;
 }
-__global__ void __launch_bounds__(256) k_lg_col_argmax(const float* __restrict__ sim, int m, int n,
-                                                        const float* __restrict__ rmax, const float* __restrict__ rlog,
-                                                        const float* __restrict__ cmax, const float* __restrict__ clog,
-                                                        const float* __restrict__ z0, const float* __restrict__ z1,
-                                                        int* __restrict__ arg) {
-  __shared__ float sv[8][32];
-  __shared__ int si[8][32];
+__global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* __restrict__ sim, int m, int n,
+                                                         const float* __restrict__ rmax, const float* __restrict__ rlog,
+                                                         const float* __restrict__ cmax, const float* __restrict__ clog,
+                                                         const float* __restrict__ l0g, const float* __restrict__ l1g,
+                                                         int* __restrict__ arg) {
+  __shared__ float sv[LG_COL_WARPS][32];
+  __shared__ int si[LG_COL_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   if (j < n) {
-    const float cm = cmax[j], cl = clog[j], l1 = logsigmoid(z1[j]);
-    for (int i = warp; i < m; i += 8) {
-      float x = sim[(size_t)i * n + j];
-      float sc = (((x - rmax[i]) - rlog[i]) + ((x - cm) - cl)) + (logsigmoid(z0[i]) + l1);
-      if (sc > bv) bv = sc, bi = i;  // rows ascend within a warp: first maximum kept
+    const float cm = cmax[j], cl = clog[j], l1 = l1g[j];
+    for (int i0 = warp; i0 < m; i0 += LG_COL_WARPS * LG_COL_UNROLL) {
+      float x[LG_COL_UNROLL], rm[LG_COL_UNROLL], rl[LG_COL_UNROLL], l0[LG_COL_UNROLL];
+#pragma unroll
+      for (int u = 0; u < LG_COL_UNROLL; ++u) {
+        const int i = i0 + u * LG_COL_WARPS;
+        const bool in = i < m;
+        x[u] = in ? sim[(size_t)i * n + j] : 0.f;
+        rm[u] = in ? rmax[i] : 0.f, rl[u] = in ? rlog[i] : 0.f, l0[u] = in ? l0g[i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < LG_COL_UNROLL; ++u) {
+        const int i = i0 + u * LG_COL_WARPS;
+        if (i < m) {
+          const float sc = (((x[u] - rm[u]) - rl[u]) + ((x[u] - cm) - cl)) + (l0[u] + l1);
+          if (sc > bv) bv = sc, bi = i;  // rows ascend within a warp: first maximum kept
+        }
+      }
     }
   }
   sv[warp][lane] = bv, si[warp][lane] = bi;
   __syncthreads();
   if (warp == 0 && j < n) {
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < LG_COL_WARPS; ++w) {
       float ov = sv[w][lane];
       int oi = si[w][lane];
       if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
@@ -528,6 +555,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   {
     const char* e = getenv("B2_FORCE_SIMT");
     s->use_tc = !(e && e[0] == '1');
@@ -571,7 +599,7 @@ static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
   B2_CUDA(ctx, sd.h.ensure(N * 512 * 4));
   B2_CUDA(ctx, sd.hs.ensure(N * 512 * 4));
   B2_CUDA(ctx, sd.md.ensure(N * 256 * 4));
-  DevBuf* small[] = {&sd.conf, &sd.mat, &sd.src, &sd.rmax, &sd.rlog, &sd.ls, &sd.amax, &sd.aidx};
+  DevBuf* small[] = {&sd.conf, &sd.mat, &sd.src, &sd.rmax, &sd.rlog, &sd.ls, &sd.lsg, &sd.amax, &sd.aidx};
   for (DevBuf* b : small) B2_CUDA(ctx, b->ensure(N * 4));
   sd.cur = 0;
   sd.n = n;
@@ -764,15 +792,17 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
   gs.cf = s->sim.as<float>(), gs.ldc = b.n, gs.tc_want_f32 = true, gs.M = a.n, gs.N = b.n;
   if ((rc = lg_linear(ctx, st, s, gs))) return rc;
   const float* sim = s->sim.as<float>();
-  B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>());
+  B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(), a.ls.as<float>(),
+            a.lsg.as<float>());
   B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 32), 256, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>());
+  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>(), b.ls.as<float>(),
+            b.lsg.as<float>());
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_lg_row_argmax, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
-            b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
+            b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
   B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
-            b.rmax.as<float>(), b.rlog.as<float>(), a.ls.as<float>(), b.ls.as<float>(), b.aidx.as<int>());
+  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+            b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), b.aidx.as<int>());
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,
             (float)prm->filter_threshold, a.ind[a.cur].as<int>(), b.ind[b.cur].as<int>(), out_matches, out_scores, counters + 4);

@@ -9,6 +9,7 @@
 #include "gemm_ws.cuh"
 #include "attn_ws.cuh"
 #include "attn_ts.cuh"
+#include "attn_ps.cuh"
 #include <cstdlib>
 
 struct TcWeights {  // a model's weight blob in fp32 and as split-fp16 planes (same element offsets in all three)
@@ -41,6 +42,14 @@ static inline bool gemm_use_ws() {
     return !(e && e[0] == '0');
   }();
   return ws;
+}
+// ... and its persistent stream-K schedule (k_flash_ps) is what runs unless B2_ATTN_PS=0
+static inline bool attn_use_ps() {
+  static const bool ps = [] {
+    const char* e = getenv("B2_ATTN_PS");
+    return !(e && e[0] == '0');
+  }();
+  return ps;
 }
 static inline bool attn_v_unscaled(const TcWeights& tw) { return attn_qk_unscaled(tw) && attn_use_ts(); }
 
@@ -186,6 +195,51 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     return launch_flash(ctx, st, b.q->as<float>(), b.k->as<float>(), b.v->as<float>(), b.o->as<float>(), b.nq, b.nk, scale);
   }
   const FlashJob* jobs[2] = {&a, &b};
+  if (tw.use_tma && tma_encoder() && tw.attn_part && attn_use_ts() && attn_use_ps()) {
+    AttnTsMaps tmaps;
+    AttnPsArgs pa{};
+    bool okm = true;
+    int items = 0;
+    for (int i = 0; i < 2; ++i) {
+      const FlashJob& j = *jobs[i];
+      const Pl q = planes_of(*j.q, (size_t)j.capq * 256), k = planes_of(*j.k, (size_t)j.capk * 256), v = planes_of(*j.v, (size_t)j.capk * 256),
+               o = planes_of(*j.o, (size_t)j.capq * 256);
+      AttnPsProblem& p = pa.p[i];
+      p.Qh = q.hi, p.Ql = q.lo, p.Oh = o.hi, p.Ol = o.lo, p.Nq = j.nq, p.Nk = j.nk;
+      p.qt = (j.nq > 0 && j.nk > 0) ? cdiv(j.nq, 2 * AW_Q) : 0, p.tiles = j.nk > 0 ? cdiv(j.nk, AW_KV) : 1;
+      items += p.qt * 4;
+      if (p.qt == 0) {  // nothing to do for this problem: mirror the other one's maps so the struct is fully initialised
+        continue;
+      }
+      okm = okm && tma_map_2d(&tmaps.kh[i], k.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&tmaps.kl[i], k.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+      okm = okm && tma_map_2d(&tmaps.vh[i], v.hi, (uint64_t)4 * j.nk, 64, 64, AW_KV) && tma_map_2d(&tmaps.vl[i], v.lo, (uint64_t)4 * j.nk, 64, 64, AW_KV);
+    }
+    if (!okm) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (attention)");
+    for (int i = 0; i < 2; ++i)
+      if (pa.p[i].qt == 0) tmaps.kh[i] = tmaps.kh[1 - i], tmaps.kl[i] = tmaps.kl[1 - i], tmaps.vh[i] = tmaps.vh[1 - i], tmaps.vl[i] = tmaps.vl[1 - i];
+    pa.W0 = pa.p[0].qt * 4 * pa.p[0].tiles;
+    pa.W = pa.W0 + pa.p[1].qt * 4 * pa.p[1].tiles;
+    if (pa.W <= 0) return B2_OK;
+    int ncta = pa.W < tw.sm_count ? pa.W : tw.sm_count;
+    pa.quota = cdiv(pa.W, ncta);
+    ncta = cdiv(pa.W, pa.quota);
+    const int tmax = pa.p[0].tiles > pa.p[1].tiles ? pa.p[0].tiles : pa.p[1].tiles;
+    pa.max_splits = cdiv(tmax, pa.quota) + 1;
+    B2_CUDA(ctx, tw.attn_part[0].ensure((size_t)items * pa.max_splits * 256 * 64 * 4));
+    B2_CUDA(ctx, tw.attn_ml[0].ensure((size_t)items * pa.max_splits * 256 * 2 * 4));
+    pa.Opart = tw.attn_part[0].as<float>(), pa.ml = tw.attn_ml[0].as<float>();
+    pa.scale = scale, pa.err_flag = tw.err;
+    b2_prof_work(ctx, "k_flash_ps", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));
+    B2_LAUNCH(ctx, k_flash_ps, ncta, AS_THREADS, AS_SMEM, st, tmaps, pa);
+    B2_CHECK_LAUNCH(ctx);
+    for (int i = 0; i < 2; ++i) {
+      const AttnPsProblem& p = pa.p[i];
+      if (p.qt == 0 || cdiv(p.tiles, pa.quota) + 1 <= 1) continue;
+      B2_LAUNCH(ctx, k_attn_merge_ps, cdiv(p.Nq * 128, 256), 256, 0, st, pa, i);
+      B2_CHECK_LAUNCH(ctx);
+    }
+    return B2_OK;
+  }
   if (tw.use_tma && tma_encoder() && tw.attn_part) {
     AttnWsMaps maps;
     AttnWsArgs wa{};
