@@ -59,7 +59,13 @@ def kernel(rep, top=18):
         return
     h = rows[1]
     ci = {n: i for i, n in enumerate(h)}
-    data = [x for x in rows[2:] if len(x) == len(h)]
+    data = []
+    for x in rows[2:]:  # a report with several launches repeats the header: keep the first launch only
+        if len(x) != len(h):
+            continue
+        if x == h:
+            break
+        data.append(x)
     stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
     tot = sum(int(x[ci["# Samples"]] or 0) for x in data)
     agg = {s: sum(int(x[ci[s]] or 0) for x in data) for s in stalls}
