@@ -7,8 +7,8 @@
 // (item, key-tile range) back to back: TMEM stays allocated, the barriers keep running phase counters, the TMA producer
 // streams the next segment's K / V tiles while the current one drains, and the next segment's Q is stored and its first
 // logits issued before the softmax warps write the current segment's result.  A segment that covers its item completely
-// writes the normalised output planes; otherwise it writes an un-normalised partial (O, m, l) that k_attn_merge_ps
-// combines (<= 2-3 partials per item instead of 4).
+// writes the normalised output planes; otherwise it writes an un-normalised partial (O, m, l), and the LAST segment of an
+// item to arrive (device-scope counter, stream-K "fix-up") combines the 2-3 partials in the same kernel.
 //
 // TMEM layout, warp roles and hand-offs are those of attn_ts.cuh; all barrier parities are functions of running counters
 // (ring entry `ge`, tile `gt`, segment `seg`) that every role advances identically.
@@ -25,6 +25,7 @@ struct AttnPsArgs {
   AttnPsProblem p[2];
   float* Opart;  // [item][max_splits][256][64] fp32, un-normalised
   float* ml;     // [item][max_splits][256][2]
+  int* arrivals; // [item][2] zero on entry; counts the partials of (item, query tile) written so far, reset by the merger
   int W0, W;     // units of problem 0, total units
   int quota;     // units per CTA
   int max_splits;
@@ -68,6 +69,7 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
   uint64_t* o_full = p_full + 2;            // [2]
   uint64_t* q_ready = o_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [2] per softmax warpgroup
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int w_begin = blockIdx.x * args.quota;
@@ -287,8 +289,8 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
       tc::tmem_ld64(tO, o);
       tc::fence_before_sync();  // our read of O is ordered before the next segment's first PV (gated by our p_full arrival)
       const int qrow = sg.q0 + q * AW_Q + r;
-      if (qrow < pr.Nq) {
-        if (sg.nsplits == 1) {
+      if (sg.nsplits == 1) {
+        if (qrow < pr.Nq) {
           const float inv = 1.0f / l_i;
           uint4* dh = reinterpret_cast<uint4*>(pr.Oh + (size_t)qrow * 256 + sg.h * 64);
           uint4* dl = reinterpret_cast<uint4*>(pr.Ol + (size_t)qrow * 256 + sg.h * 64);
@@ -300,14 +302,58 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
             dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-        } else {
-          const size_t slot = (size_t)sg.itemg * args.max_splits + sg.split;
-          float4* dst = reinterpret_cast<float4*>(args.Opart + (slot * 256 + q * AW_Q + r) * 64);
+        }
+      } else {
+        // partial of a cut item; the warpgroup that completes the item (last to arrive) merges all of them
+        const size_t slot0 = (size_t)sg.itemg * args.max_splits;
+        const size_t rowi = (slot0 + sg.split) * 256 + q * AW_Q + r;
+        if (qrow < pr.Nq) {
+          float4* dst = reinterpret_cast<float4*>(args.Opart + rowi * 64);
 #pragma unroll
           for (int c = 0; c < 16; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-          float* ml = args.ml + (slot * 256 + q * AW_Q + r) * 2;
-          ml[0] = m_ref;
-          ml[1] = l_i;
+          *reinterpret_cast<float2*>(args.ml + rowi * 2) = make_float2(m_ref, l_i);
+        }
+        __threadfence();  // partial visible device-wide before this warpgroup is counted
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        if (r == 0) {
+          int* cnt = args.arrivals + sg.itemg * 2 + q;
+          const int old = atomicAdd(cnt, 1);
+          const int last = old == sg.nsplits - 1;
+          if (last) atomicExch(cnt, 0);  // nobody else touches it in this launch; zero again for the next one
+          last_flag[q] = last;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        if (last_flag[q] && qrow < pr.Nq) {
+          __threadfence();
+          float m = -INFINITY;
+          for (int sp = 0; sp < sg.nsplits; ++sp) m = fmaxf(m, __ldcg(args.ml + ((slot0 + sp) * 256 + q * AW_Q + r) * 2));
+          float l = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) o[j] = 0.f;
+          for (int sp = 0; sp < sg.nsplits; ++sp) {
+            const size_t ri = (slot0 + sp) * 256 + q * AW_Q + r;
+            const float2 mlv = __ldcg(reinterpret_cast<const float2*>(args.ml + ri * 2));
+            const float wgt = tc::ex2(mlv.x - m);
+            l = fmaf(mlv.y, wgt, l);
+            const float4* src = reinterpret_cast<const float4*>(args.Opart + ri * 64);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float4 v = __ldcg(src + c);
+              o[4 * c] = fmaf(v.x, wgt, o[4 * c]), o[4 * c + 1] = fmaf(v.y, wgt, o[4 * c + 1]);
+              o[4 * c + 2] = fmaf(v.z, wgt, o[4 * c + 2]), o[4 * c + 3] = fmaf(v.w, wgt, o[4 * c + 3]);
+            }
+          }
+          const float inv = 1.0f / l;
+          uint4* dh = reinterpret_cast<uint4*>(pr.Oh + (size_t)qrow * 256 + sg.h * 64);
+          uint4* dl = reinterpret_cast<uint4*>(pr.Ol + (size_t)qrow * 256 + sg.h * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+            dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
     }
@@ -319,32 +365,3 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
   if (warp == 9) tc::tmem_dealloc(tmem, 512);
 }
 
-// combine the partials of items that were cut across CTAs; one thread per (problem row, head, column pair)
-static __global__ void __launch_bounds__(256) k_attn_merge_ps(AttnPsArgs a, int z) {
-  const AttnPsProblem& p = a.p[z];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over Nq * 4 heads * 32 column pairs
-  if (idx >= p.Nq * 128) return;
-  const int cp = idx & 31, h = (idx >> 5) & 3, qrow = idx >> 7;
-  const int item = h * p.qt + qrow / (2 * AW_Q), rr = qrow % (2 * AW_Q);
-  const int wi0 = (z ? a.W0 : 0) + item * p.tiles, wi1 = wi0 + p.tiles;
-  const int c_first = wi0 / a.quota;
-  const int ns = (wi1 - 1) / a.quota - c_first + 1;
-  if (ns == 1) return;  // written in final form by the attention kernel
-  const size_t slot0 = (size_t)((z ? a.p[0].qt * 4 : 0) + item) * a.max_splits;
-  float m = -INFINITY;
-  for (int s = 0; s < ns; ++s) m = fmaxf(m, a.ml[((slot0 + s) * 256 + rr) * 2]);
-  float l = 0.f, x = 0.f, y = 0.f;
-  for (int s = 0; s < ns; ++s) {
-    const float* q = a.ml + ((slot0 + s) * 256 + rr) * 2;
-    const float wgt = tc::ex2(q[0] - m);
-    l = fmaf(q[1], wgt, l);
-    const float2 v = *reinterpret_cast<const float2*>(a.Opart + ((slot0 + s) * 256 + rr) * 64 + 2 * cp);
-    x = fmaf(v.x, wgt, x);
-    y = fmaf(v.y, wgt, y);
-  }
-  const float inv = 1.0f / l;
-  uint32_t hi, lo;
-  tc::split2(x * inv, y * inv, hi, lo);
-  *reinterpret_cast<uint32_t*>(p.Oh + (size_t)qrow * 256 + h * 64 + 2 * cp) = hi;
-  *reinterpret_cast<uint32_t*>(p.Ol + (size_t)qrow * 256 + h * 64 + 2 * cp) = lo;
-}

@@ -82,8 +82,9 @@ void lg_destroy(b2_context* ctx) {
 // kernels
 // ------------------------------------------------------------------------------------------------------------------
 
-// normalize_keypoints with size=None (lightglue.py:31-43) + LearnableFourierPositionalEncoding (:68-81), one block.
-// Also initialises ind[n] = n.
+// normalize_keypoints with size=None (lightglue.py:31-43) + LearnableFourierPositionalEncoding (:68-81).  Every block
+// re-derives the bounding box (40 KB of keypoints, L2-resident) and then takes a grid-stride share of the n x 32
+// (cos, sin) table.  Also initialises ind[n] = n.
 __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp, int n, const float* __restrict__ wr /*[32][2]*/,
                                                      float* __restrict__ cs, float* __restrict__ sn, int* __restrict__ ind) {
   __shared__ float red[4][32];
@@ -105,14 +106,15 @@ __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp
   // size = 1 + max - min ; shift = size / 2 ; scale = max(size) / 2
   const float sx = 1.0f + bb[2] - bb[0], sy = 1.0f + bb[3] - bb[1];
   const float shx = sx / 2.0f, shy = sy / 2.0f, sc = fmaxf(sx, sy) / 2.0f;
-  for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (int i = gtid; i < n * 32; i += gsz) {
     int p = i >> 5, f = i & 31;
     float x = (kp[2 * p] - shx) / sc, y = (kp[2 * p + 1] - shy) / sc;
     float pr = x * wr[2 * f] + y * wr[2 * f + 1];
     cs[i] = cosf(pr);
     sn[i] = sinf(pr);
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ind[i] = i;
+  for (int i = gtid; i < n; i += gsz) ind[i] = i;
 }
 
 // qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64],
@@ -715,7 +717,7 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
       B2_LAUNCH(ctx, k_split_f32, (unsigned)cdiv(ns[i] * 256, 256), 256, 0, st, descs[i], (size_t)ns[i] * 256, xp.hi, xp.lo);
       B2_CHECK_LAUNCH(ctx);
     }
-    B2_LAUNCH(ctx, k_lg_posenc, 1, 1024, 0, st, kps[i], ns[i], s->wr, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>());
+    B2_LAUNCH(ctx, k_lg_posenc, ns[i] * 32 <= 1024 ? 1 : (cdiv(ns[i] * 32, 1024) < 148 ? cdiv(ns[i] * 32, 1024) : 148), 1024, 0, st, kps[i], ns[i], s->wr, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>());
     B2_CHECK_LAUNCH(ctx);
   }
   const bool do_stop = prm->depth_confidence > 0.0, do_prune = prm->width_confidence > 0.0;

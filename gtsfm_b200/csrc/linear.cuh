@@ -227,17 +227,20 @@ static int run_flash2(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     pa.max_splits = cdiv(tmax, pa.quota) + 1;
     B2_CUDA(ctx, tw.attn_part[0].ensure((size_t)items * pa.max_splits * 256 * 64 * 4));
     B2_CUDA(ctx, tw.attn_ml[0].ensure((size_t)items * pa.max_splits * 256 * 2 * 4));
+    {  // arrival counters: zero once per allocation, the kernel leaves them zero
+      DevBuf& cnt = tw.attn_ml[1];
+      const size_t need = (size_t)items * 2 * sizeof(int);
+      if (cnt.cap < need) {
+        B2_CUDA(ctx, cnt.ensure(need * 4));
+        B2_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, cnt.cap, st));
+      }
+      pa.arrivals = cnt.as<int>();
+    }
     pa.Opart = tw.attn_part[0].as<float>(), pa.ml = tw.attn_ml[0].as<float>();
     pa.scale = scale, pa.err_flag = tw.err;
     b2_prof_work(ctx, "k_flash_ps", 4.0 * 2.0 * 2.0 * 64 * ((double)a.nq * a.nk + (double)b.nq * b.nk));
     B2_LAUNCH(ctx, k_flash_ps, ncta, AS_THREADS, AS_SMEM, st, tmaps, pa);
     B2_CHECK_LAUNCH(ctx);
-    for (int i = 0; i < 2; ++i) {
-      const AttnPsProblem& p = pa.p[i];
-      if (p.qt == 0 || cdiv(p.tiles, pa.quota) + 1 <= 1) continue;
-      B2_LAUNCH(ctx, k_attn_merge_ps, cdiv(p.Nq * 128, 256), 256, 0, st, pa, i);
-      B2_CHECK_LAUNCH(ctx);
-    }
     return B2_OK;
   }
   if (tw.use_tma && tma_encoder() && tw.attn_part) {
