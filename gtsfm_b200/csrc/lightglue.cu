@@ -119,11 +119,23 @@ __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp
 
 // qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64],
 // either as fp32 (SIMT attention) or split into fp16 hi / lo planes (tcgen05 attention; plane stride = 4*N*64 halves).
+struct RotJob {  // one image's share of a two-image launch (blockIdx.y)
+  const float *qkv, *cs, *sn;
+  int n;
+  size_t plane;
+  void *qo, *ko, *vo;
+};
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict__ qkv, const float* __restrict__ cs,
-                                                          const float* __restrict__ sn, int n, size_t plane,
-                                                          void* __restrict__ qo, void* __restrict__ ko, void* __restrict__ vo,
-                                                          int qk_unscaled) {
+__global__ void __launch_bounds__(256) k_lg_split_rotary(RotJob j0, RotJob j1, int qk_unscaled) {
+  const RotJob& jb = blockIdx.y ? j1 : j0;
+  const float* __restrict__ qkv = jb.qkv;
+  const float* __restrict__ cs = jb.cs;
+  const float* __restrict__ sn = jb.sn;
+  const int n = jb.n;
+  const size_t plane = jb.plane;
+  void* __restrict__ qo = jb.qo;
+  void* __restrict__ ko = jb.ko;
+  void* __restrict__ vo = jb.vo;
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n * 4 * 32 pairs
   if (i >= n * 128) return;
   int p = i & 31, h = (i >> 5) & 3, r = i >> 7;
@@ -158,9 +170,17 @@ __global__ void __launch_bounds__(256) k_lg_split_rotary(const float* __restrict
 
 // LayerNorm(512, eps 1e-5, affine) + exact GELU in place (lightglue.py:152-157). one warp per row.
 // When `hi` is given the result is written as split fp16 planes (the next GEMM's A operand) instead of in place.
-__global__ void __launch_bounds__(256) k_lg_ln_gelu(float* __restrict__ h, int n, const float* __restrict__ g,
-                                                     const float* __restrict__ b, __half* __restrict__ hi,
-                                                     __half* __restrict__ lo) {
+struct LnJob {  // one image's share of a two-image launch (blockIdx.y)
+  float* h;
+  int n;
+  __half *hi, *lo;
+};
+__global__ void __launch_bounds__(256) k_lg_ln_gelu(LnJob j0, LnJob j1, const float* __restrict__ g, const float* __restrict__ b) {
+  const LnJob& jb = blockIdx.y ? j1 : j0;
+  float* __restrict__ h = jb.h;
+  __half* __restrict__ hi = jb.hi;
+  __half* __restrict__ lo = jb.lo;
+  const int n = jb.n;
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= n) return;
   float4* row = reinterpret_cast<float4*>(h + (size_t)r * 512);
@@ -633,12 +653,19 @@ static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, c
   }
   if ((rc = lg_linear(ctx, st, s, o[0], &o[1]))) return rc;
   if ((rc = lg_linear(ctx, st, s, f0[0], &f0[1]))) return rc;
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    const Pl hs = planes_of(sd.hs, (size_t)sd.cap * 512);
-    B2_LAUNCH(ctx, k_lg_ln_gelu, cdiv(sd.n, 8), 256, 0, st, sd.h.as<float>(), sd.n, lng, lnb, s->use_tc ? hs.hi : (__half*)nullptr,
-              s->use_tc ? hs.lo : (__half*)nullptr);
-    B2_CHECK_LAUNCH(ctx);
+  {
+    LnJob lj[2];
+    int mx = 0;
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
+      const Pl hs = planes_of(sd.hs, (size_t)sd.cap * 512);
+      lj[i] = {sd.h.as<float>(), sd.n, s->use_tc ? hs.hi : (__half*)nullptr, s->use_tc ? hs.lo : (__half*)nullptr};
+      mx = sd.n > mx ? sd.n : mx;
+    }
+    if (mx > 0) {
+      B2_LAUNCH(ctx, k_lg_ln_gelu, dim3(cdiv(mx, 8), 2), 256, 0, st, lj[0], lj[1], lng, lnb);
+      B2_CHECK_LAUNCH(ctx);
+    }
   }
   return lg_linear(ctx, st, s, f3[0], &f3[1]);
 }
@@ -654,16 +681,22 @@ static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, in
     a.w = w.wqkv, a.ldb = 256, a.bias = w.bqkv, a.cf = sd.qkv.as<float>(), a.ldc = 768, a.tc_want_f32 = true, a.M = sd.n, a.N = 768;
   }
   if ((rc = lg_linear(ctx, st, s, q[0], &q[1]))) return rc;
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    const int n = sd.n;
-    if (s->use_tc)
-      B2_LAUNCH(ctx, k_lg_split_rotary<true>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, (attn_qk_unscaled(lg_tw(s)) ? 1 : 0) | (attn_v_unscaled(lg_tw(s)) ? 2 : 0));
-    else
-      B2_LAUNCH(ctx, k_lg_split_rotary<false>, cdiv(n * 128, 256), 256, 0, st, sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(),
-                sd.sn[sd.cur].as<float>(), n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p, 0);
-    B2_CHECK_LAUNCH(ctx);
+  {
+    RotJob rj[2];
+    int mx = 0;
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
+      rj[i] = {sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p};
+      mx = sd.n > mx ? sd.n : mx;
+    }
+    if (mx > 0) {
+      if (s->use_tc)
+        B2_LAUNCH(ctx, k_lg_split_rotary<true>, dim3(cdiv(mx * 128, 256), 2), 256, 0, st, rj[0], rj[1],
+                  (attn_qk_unscaled(lg_tw(s)) ? 1 : 0) | (attn_v_unscaled(lg_tw(s)) ? 2 : 0));
+      else
+        B2_LAUNCH(ctx, k_lg_split_rotary<false>, dim3(cdiv(mx * 128, 256), 2), 256, 0, st, rj[0], rj[1], 0);
+      B2_CHECK_LAUNCH(ctx);
+    }
   }
   LgSide &a = s->side[0], &b = s->side[1];
   FlashJob ja{&a.q, &a.k, &a.v, &a.ctx, a.n, a.n, a.cap, a.cap}, jb{&b.q, &b.k, &b.v, &b.ctx, b.n, b.n, b.cap, b.cap};
@@ -746,15 +779,6 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
       B2_LAUNCH(ctx, k_lg_prune_plan, 1, 1024, 0, st, sd.conf.as<float>(), sd.mat.as<float>(), sd.n,
                 do_stop ? s->thr[layer] : -1.0f, keep_thr, i, sd.src.as<int>(), counters);
       B2_CHECK_LAUNCH(ctx);
-      if (prune_side[i]) {
-        int nxt = sd.cur ^ 1;
-        B2_LAUNCH(ctx, k_lg_gather, cdiv(sd.n, 8), 256, 0, st, sd.src.as<int>(), counters + 2 + i, x,
-                  sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(),
-                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>(),
-                  s->use_tc ? sd.xs[sd.cur].as<__half>() : (const __half*)nullptr, (size_t)sd.cap * 256, sd.xs[nxt].as<__half>(),
-                  (size_t)sd.cap * 256);
-        B2_CHECK_LAUNCH(ctx);
-      }
     }
     B2_CUDA(ctx, cudaMemcpyAsync(hread, counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(ctx, cudaStreamSynchronize(st));
@@ -763,11 +787,22 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
       float ratio = 1.0f - (float)(hread[0] + hread[1]) / (float)(n0 + n1);
       if (ratio > (float)prm->depth_confidence) break;
     }
-    for (int i = 0; i < 2; ++i)
-      if (prune_side[i]) {
-        s->side[i].cur ^= 1;
-        s->side[i].n = hread[2 + i];
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
+      if (!prune_side[i] || hread[2 + i] == sd.n) continue;  // nothing pruned: the buffers stay as they are
+      const float* x = sd.x[sd.cur].as<float>();
+      {
+        int nxt = sd.cur ^ 1;
+        B2_LAUNCH(ctx, k_lg_gather, cdiv(sd.n, 8), 256, 0, st, sd.src.as<int>(), counters + 2 + i, x,
+                  sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(),
+                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>(),
+                  s->use_tc ? sd.xs[sd.cur].as<__half>() : (const __half*)nullptr, (size_t)sd.cap * 256, sd.xs[nxt].as<__half>(),
+                  (size_t)sd.cap * 256);
+        B2_CHECK_LAUNCH(ctx);
       }
+      sd.cur ^= 1;
+      sd.n = hread[2 + i];
+    }
   }
   if (layer == LG_LAYERS) layer = LG_LAYERS - 1;
   *out_stop = layer + 1;
