@@ -35,6 +35,8 @@ SIGNATURES = {
     "b2_destroy": (None, [_vp]),
     "b2_last_error": (C.c_char_p, [_vp]),
     "b2_launch_count": (C.c_uint64, [_vp]),
+    "b2_h2d_bytes": (C.c_uint64, [_vp]),
+    "b2_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "b2_profile_start": (_i, [_vp, C.c_char_p]),
     "b2_profile_stop": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "b2_debug_fetch": (C.c_int64, [_vp, C.c_char_p, _vp, C.c_int64]),
@@ -110,6 +112,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.b2_launch_count(self.handle))
+
+    def set_option(self, name: str, value: int) -> None:
+        self.check(self._lib.b2_set_option(self.handle, name.encode(), int(value)), f"set_option({name})")
+
+    def h2d_bytes(self) -> int:
+        return int(self._lib.b2_h2d_bytes(self.handle))
 
     def profile_start(self, kernel_prefix: str) -> None:
         self.check(self._lib.b2_profile_start(self.handle, kernel_prefix.encode()), "profile_start")

@@ -1,4 +1,6 @@
 // Context lifecycle and shared C-ABI entry points.
+#include <string.h>
+
 #include "common.cuh"
 
 extern "C" int b2_version(void) { return 100; }
@@ -41,6 +43,17 @@ extern "C" void b2_destroy(b2_context* ctx) {
 extern "C" const char* b2_last_error(const b2_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" uint64_t b2_launch_count(const b2_context* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int b2_set_option(b2_context* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!strcmp(name, "reserve_sms")) {
+    if (value < 0 || value >= ctx->sm_count) return b2_fail(ctx, B2_ERR_ARG, "reserve_sms out of range");
+    ctx->reserve_sms = (int)value;
+    return B2_OK;
+  }
+  return b2_fail(ctx, B2_ERR_ARG, std::string("unknown option ") + name);
+}
+extern "C" uint64_t b2_h2d_bytes(const b2_context* ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 extern "C" int64_t b2_debug_fetch(b2_context* ctx, const char* name, float* host_out, int64_t max_floats) {
   if (!ctx || !name || !host_out) return B2_ERR_ARG;

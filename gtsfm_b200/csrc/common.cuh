@@ -82,9 +82,23 @@ struct LightGlueState;
 struct SuperGlueState;
 struct RansacState;
 
+// Device copies of host feature arrays handed to the *_host matcher entry points.  GTSfM matches one image's (keypoints,
+// descriptors) against ~20-40 partners, always passing the same host arrays, so re-uploading 5 MB per image per pair is
+// most of the plugin path's PCIe traffic.  An entry is keyed by (host pointer, size) and validated by a signature over
+// ~600 sampled words, so a freed-and-reused address or rewritten array is re-uploaded.  B2_FEATURE_CACHE=0 disables it.
+struct FeatCacheEntry {
+  const void* host = nullptr;
+  size_t bytes = 0;
+  uint64_t sig = 0;
+  uint64_t stamp = 0;
+  DevBuf buf;
+};
+constexpr int B2_FEAT_CACHE_SLOTS = 96;
+
 struct b2_context {
   int device = 0;
   int sm_count = 148;
+  int reserve_sms = 0;  // SMs the persistent kernels of this context leave free (b2_set_option "reserve_sms")
   std::string err;
   std::mutex mu;
   uint64_t launches = 0;
@@ -98,6 +112,10 @@ struct b2_context {
   // staging shared by the *_host entry points
   DevBuf stage_d[8];
   HostBuf stage_h[4];
+  FeatCacheEntry fcache[B2_FEAT_CACHE_SLOTS];
+  uint64_t fstamp = 0;
+  int fcache_on = -1;          // -1 = read B2_FEATURE_CACHE on first use
+  uint64_t h2d_bytes = 0;      // bytes the *_host entry points that track them actually copied
 };
 
 inline int b2_fail(b2_context* ctx, int code, const std::string& msg) {

@@ -41,6 +41,7 @@ struct LgSide {  // per-image workspace
 
 struct LightGlueState {
   bool loaded = false;
+  int persist_ctas = 148;  // CTAs of the persistent kernels = SMs of the device minus the context's reserve_sms
   DevBuf wblob, wblob_h, wblob_l, errflag;  // fp32 weights + their split-fp16 (hi, lo * 2^11) copies for tcgen05
   bool use_tc = true;                          // B2_FORCE_SIMT=1 keeps every GEMM on the exact-fp32 SIMT kernel
   float* wr = nullptr;
@@ -593,7 +594,7 @@ static inline TcWeights lg_tw(LightGlueState* s) {
   TcWeights t{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
   const char* e = getenv("B2_NO_TMA");
   t.use_tma = !(e && e[0] == '1');
-  t.attn_part = s->attn_part, t.attn_ml = s->attn_ml;
+  t.attn_part = s->attn_part, t.attn_ml = s->attn_ml, t.sm_count = s->persist_ctas;
   return t;
 }
 static int lg_linear(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LinArgs& a, const LinArgs* b = nullptr) {
@@ -734,6 +735,7 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
                          float* out_scores, int* out_k, int* out_stop, cudaStream_t st) {
   LightGlueState* s = ctx->lg;
   if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "lightglue weights not set");
+  s->persist_ctas = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
   *out_k = 0;
   *out_stop = 1;
   if (n0 <= 0 || n1 <= 0) return B2_OK;  // lightglue.py:568-588 (no keypoints -> empty matches)
@@ -869,6 +871,52 @@ extern "C" int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const f
                        out_stop_layer, (cudaStream_t)stream);
 }
 
+
+// 64-bit FNV-1a over ~600 words sampled across the array (head, tail and an even stride): the identity check of the
+// feature cache
+static uint64_t b2_feat_signature(const void* host, size_t bytes) {
+  const uint32_t* w = static_cast<const uint32_t*>(host);
+  const size_t n = bytes / 4;
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)bytes;
+  auto mix = [&](uint32_t v) { h = (h ^ v) * 1099511628211ull; };
+  const size_t edge = n < 32 ? n : 32;
+  for (size_t i = 0; i < edge; ++i) mix(w[i]), mix(w[n - 1 - i]);
+  const size_t step = n / 512 ? n / 512 : 1;
+  for (size_t i = 0; i < n; i += step) mix(w[i]);
+  return h;
+}
+// Device address of a host array: from the cache when the same (pointer, size, signature) was uploaded before, else
+// copied (into an LRU cache slot, or into `fallback` when the cache is off).
+static int b2_upload_cached(b2_context* ctx, const void* host, size_t bytes, DevBuf* fallback, cudaStream_t st, const void** dev) {
+  if (ctx->fcache_on < 0) {
+    const char* e = getenv("B2_FEATURE_CACHE");
+    ctx->fcache_on = !(e && e[0] == '0');
+  }
+  if (!ctx->fcache_on || bytes < 4) {
+    B2_CUDA(ctx, fallback->ensure(bytes));
+    B2_CUDA(ctx, cudaMemcpyAsync(fallback->p, host, bytes, cudaMemcpyHostToDevice, st));
+    ctx->h2d_bytes += bytes;
+    *dev = fallback->p;
+    return B2_OK;
+  }
+  const uint64_t sig = b2_feat_signature(host, bytes);
+  FeatCacheEntry* lru = &ctx->fcache[0];
+  for (FeatCacheEntry& e : ctx->fcache) {
+    if (e.host == host && e.bytes == bytes && e.sig == sig) {
+      e.stamp = ++ctx->fstamp;
+      *dev = e.buf.p;
+      return B2_OK;
+    }
+    if (e.stamp < lru->stamp) lru = &e;
+  }
+  B2_CUDA(ctx, lru->buf.ensure(bytes));  // (cudaFree inside ensure synchronises: no kernel still reads the old block)
+  B2_CUDA(ctx, cudaMemcpyAsync(lru->buf.p, host, bytes, cudaMemcpyHostToDevice, st));
+  ctx->h2d_bytes += bytes;
+  lru->host = host, lru->bytes = bytes, lru->sig = sig, lru->stamp = ++ctx->fstamp;
+  *dev = lru->buf.p;
+  return B2_OK;
+}
+
 extern "C" int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
                                        const float* desc1, int n1, const b2_lightglue_params* params,
                                        int64_t* out_matches, float* out_scores, int* out_k, int* out_stop_layer) {
@@ -881,18 +929,23 @@ extern "C" int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const 
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const int mk = n0 < n1 ? n0 : n1;
-  B2_CUDA(ctx, ctx->stage_d[0].ensure((size_t)n0 * 2 * 4));
-  B2_CUDA(ctx, ctx->stage_d[1].ensure((size_t)n0 * 256 * 4));
-  B2_CUDA(ctx, ctx->stage_d[2].ensure((size_t)n1 * 2 * 4));
-  B2_CUDA(ctx, ctx->stage_d[3].ensure((size_t)n1 * 256 * 4));
   B2_CUDA(ctx, ctx->stage_d[5].ensure((size_t)mk * 2 * 8));
   B2_CUDA(ctx, ctx->stage_d[6].ensure((size_t)mk * 4));
-  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[0].p, kp0, (size_t)n0 * 2 * 4, cudaMemcpyHostToDevice, st));
-  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[1].p, desc0, (size_t)n0 * 256 * 4, cudaMemcpyHostToDevice, st));
-  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[2].p, kp1, (size_t)n1 * 2 * 4, cudaMemcpyHostToDevice, st));
-  B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[3].p, desc1, (size_t)n1 * 256 * 4, cudaMemcpyHostToDevice, st));
-  int rc = lg_match_impl(ctx, ctx->stage_d[0].as<float>(), ctx->stage_d[1].as<float>(), n0, ctx->stage_d[2].as<float>(),
-                         ctx->stage_d[3].as<float>(), n1, params, ctx->stage_d[5].as<long long>(),
+  const float* dkp[2];
+  const float* ddesc[2];
+  {
+    const float* hk[2] = {kp0, kp1};
+    const float* hd[2] = {desc0, desc1};
+    const int nn[2] = {n0, n1};
+    for (int i = 0; i < 2; ++i) {
+      const void *a = nullptr, *b = nullptr;
+      int rc2;
+      if ((rc2 = b2_upload_cached(ctx, hk[i], (size_t)nn[i] * 2 * 4, &ctx->stage_d[2 * i], st, &a))) return rc2;
+      if ((rc2 = b2_upload_cached(ctx, hd[i], (size_t)nn[i] * 256 * 4, &ctx->stage_d[2 * i + 1], st, &b))) return rc2;
+      dkp[i] = static_cast<const float*>(a), ddesc[i] = static_cast<const float*>(b);
+    }
+  }
+  int rc = lg_match_impl(ctx, dkp[0], ddesc[0], n0, dkp[1], ddesc[1], n1, params, ctx->stage_d[5].as<long long>(),
                          ctx->stage_d[6].as<float>(), out_k, out_stop_layer, st);
   if (rc) return rc;
   if (*out_k > 0) {

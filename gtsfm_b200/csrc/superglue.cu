@@ -355,7 +355,7 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
   {
     const char* e = getenv("B2_NO_TMA");
     tw.use_tma = !(e && e[0] == '1');
-    tw.attn_part = s->attn_part, tw.attn_ml = s->attn_ml, tw.sm_count = ctx->sm_count;
+    tw.attn_part = s->attn_part, tw.attn_ml = s->attn_ml, tw.sm_count = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
   }
   int rc;
   const float* kps[2] = {kp0, kp1};

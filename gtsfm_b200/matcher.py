@@ -39,12 +39,13 @@ class LightGlueEngine:
         sc = np.empty(cap, np.float32)
         k, stop = _lib.C.c_int(0), _lib.C.c_int(0)
         prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, prune_min_kpts)
+        sent0 = self.ctx.h2d_bytes()
         rc = self.ctx.lib.b2_lightglue_match_host(self.ctx.handle, _lib.ptr(kp0), _lib.ptr(desc0), n0, _lib.ptr(kp1),
                                                   _lib.ptr(desc1), n1, _lib.C.byref(prm), _lib.ptr(out), _lib.ptr(sc),
                                                   _lib.C.byref(k), _lib.C.byref(stop))
         self.ctx.check(rc, "lightglue_match")
         self.last_stop = stop.value
-        self.h2d_bytes += kp0.nbytes + kp1.nbytes + desc0.nbytes + desc1.nbytes
+        self.h2d_bytes += self.ctx.h2d_bytes() - sent0  # feature arrays the library already holds are not re-sent
         self.d2h_bytes += k.value * (16 + 4) + 8
         if return_scores:
             return out[: k.value].copy(), sc[: k.value].copy()

@@ -29,6 +29,9 @@ class DeviceFeatures:
         return int(self.kp.shape[0])
 
 
+RESERVE_SMS_FOR_VERIFY = 8  # k_rs_hyp_E: 1000 hypotheses / 128 threads = 8 CTAs for ~1 ms
+
+
 class DeviceFrontEnd:
     def __init__(self, superpoint_sd, lightglue_sd=None, device: int = 0, max_keypoints: int = 5000, cpu_semantics: bool = True,
                  ctx: Optional[_lib.Context] = None):
@@ -102,6 +105,9 @@ class DeviceFrontEnd:
             self._vctx = _lib.Context(self.device.index)
             self._vstream = torch.cuda.Stream(self.device)
             self._vpool = ThreadPoolExecutor(max_workers=1)
+            # the matcher's persistent kernels (one CTA per SM) leave a few SMs to the concurrent RANSAC kernels: a CTA
+            # that finds its SM occupied would wait for a whole CTA lifetime and double the kernel's duration
+            self.ctx.set_option("reserve_sms", RESERVE_SMS_FOR_VERIFY)
         return self._vpool.submit(self.verify, a, b, matches, cal1, cal2, threshold_px, seed, self._vctx, self._vstream)
 
     def verify(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1: Sequence[float], cal2: Sequence[float],

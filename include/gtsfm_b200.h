@@ -41,6 +41,13 @@ void b2_destroy(b2_context* ctx);
 const char* b2_last_error(const b2_context* ctx);
 /* Number of kernels this library has launched through `ctx` since creation (bench.py's "gpu_launches"). */
 uint64_t b2_launch_count(const b2_context* ctx);
+/* Host-to-device bytes actually copied so far by the entry points that keep device copies of their host inputs
+ * (b2_lightglue_match_host: feature arrays already uploaded for an earlier pair are not sent again). */
+uint64_t b2_h2d_bytes(const b2_context* ctx);
+/* Tuning knobs.  "reserve_sms" = n: the persistent kernels (attention, GEMM) launch sm_count - n CTAs, leaving n SMs to
+ * kernels of OTHER contexts / streams running concurrently (the batched front-end overlaps pair k's RANSAC with pair
+ * k+1's matching; a one-CTA-per-SM kernel that finds an SM busy would otherwise wait for a whole CTA lifetime). */
+int b2_set_option(b2_context* ctx, const char* name, int64_t value);
 /* Live kernel timing for roofline reporting: CUDA events on the launching stream around every launch whose kernel name
  * starts with `kernel_prefix` (e.g. "k_flash_attn"), until b2_profile_stop, which returns the summed device time, the
  * number of such launches and the algorithmic work (FLOP) they performed. */

@@ -116,3 +116,24 @@ def test_plugin_contract(tmp_path, golden_dir):
     assert matcher.match(k0, empty, d0, np.zeros((0, 256), np.float32), (480, 640, 3), (480, 640, 3)).size == 0
     with pytest.raises(ValueError):
         matcher.match(Keypoints(kp0), k1, d0, d1, (480, 640, 3), (480, 640, 3))
+
+
+def test_feature_cache_reuses_and_revalidates(b200_ctx, golden_dir):
+    """b2_lightglue_match_host keeps device copies of the host feature arrays (GTSfM matches one image against many
+    partners): a repeated call sends nothing, a rewritten array at the same address is detected and sent again."""
+    fx = np.load(golden_dir / "lightglue_full_5.npz")
+    kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
+    eng = engine(b200_ctx, str(fx["profile"]))
+    m1 = eng.match(kp0, d0, kp1, d1)
+    sent = eng.h2d_bytes
+    m2 = eng.match(kp0, d0, kp1, d1)
+    assert np.array_equal(m1, fx["matches"]) and np.array_equal(m2, m1)
+    assert eng.h2d_bytes == sent, "second call with the same arrays must not upload anything"
+    # same buffers, new contents: swap the roles of the two images in place (shapes permitting) -> must re-upload
+    keep = d1.copy()
+    d1[:] = d1[::-1]
+    m3 = eng.match(kp0, d0, kp1, d1)
+    assert eng.h2d_bytes == sent + d1.nbytes, "a rewritten array must be sent again (and only that one)"
+    d1[:] = keep
+    m4 = eng.match(kp0, d0, kp1, d1)
+    assert np.array_equal(m4, m1) and not np.array_equal(m3, m1)
