@@ -261,15 +261,20 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           m_ref = m_new;
         }
         uint32_t ph[32], pl[32];
-        float rs = 0.f;
+        float2 rs2 = make_float2(0.f, 0.f);
+        const float2 c22 = make_float2(c2, c2), nm2 = make_float2(-m_ref, -m_ref), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const float pa = tc::ex2(fmaf(a[2 * jj], c2, -m_ref));
-          const float pb = tc::ex2(fmaf(a[2 * jj + 1], c2, -m_ref));
-          rs += pa + pb;
-          tc::split2_unscaled(pa, pb, ph[jj], pl[jj]);
+        for (int jj = 0; jj < 32; ++jj) {  // packed fp32 pairs: the softmax warps are issue-slot bound
+          const float2 e = tc::ffma2(make_float2(a[2 * jj], a[2 * jj + 1]), c22, nm2);
+          const float2 p2 = make_float2(tc::ex2(e.x), tc::ex2(e.y));
+          rs2 = tc::fadd2(rs2, p2);
+          const __half2 hh = __floats2half2_rn(p2.x, p2.y);
+          const float2 d = tc::ffma2(__half22float2(hh), neg1, p2);  // p - hi, exact
+          const __half2 ll = __floats2half2_rn(d.x, d.y);
+          ph[jj] = *reinterpret_cast<const uint32_t*>(&hh);
+          pl[jj] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        l_i += rs;
+        l_i += rs2.x + rs2.y;
         h_s = (i + 1 < T) && tc::mbar_test(&s_full[q * 2 + ((gi + 1) & 1)], ((gi + 1) >> 1) & 1);
         tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
         tc::tmem_st32(tS + 32, pl);

@@ -239,6 +239,27 @@ __device__ __forceinline__ void split2_unscaled(float a, float b, uint32_t& hi, 
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// ---- packed fp32 pairs (FFMA2 / FADD2: two IEEE fp32 operations per issue slot on sm_100) -----------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+  return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+  return r;
+}
+
 // canonical-layout byte offset of (row r, k-chunk c) in a tile of `rows` rows
 __device__ __forceinline__ uint32_t canon_off(int r, int c, int rows) {
   return (uint32_t)c * (uint32_t)(rows / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
