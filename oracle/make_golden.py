@@ -187,6 +187,30 @@ def golden_verifier():
               f"{verifier_ref.rot_angle_deg(R, Rc):.3f} deg, F inliers {len(rowsf)}")
 
 
+def golden_verifier_argoverse():
+    """The reference's own known-answer test for this path (tests/frontend/verifier/test_verifier_argoverse.py:32-104): 20
+    hand-labelled correspondences of an Argoverse front-centre image pair, the log's intrinsics, the expected relative pose
+    (Euler zyx [-0.37, 32.47, -0.42] deg +-1, i1ti2 [0.21, -0.0024, 0.976] +-0.01) at a 0.5 px threshold.  The labelled
+    points (test DATA of the reference, 20 x 4 numbers) are stored as a fixture together with what cv2 returns for them."""
+    import pickle
+
+    import cv2
+
+    src = Path("/root/reference/tests/data/argoverse/labeled_correspondences/argoverse_315975640448534784__315975643412234000.pkl")
+    with open(src, "rb") as f:
+        d = pickle.load(f)
+    uv1 = np.stack([np.array(d["x1"]), np.array(d["y1"])], -1).astype(np.float32)  # test_verifier_argoverse.py:51-52
+    uv2 = np.stack([np.array(d["x2"]), np.array(d["y2"])], -1).astype(np.float32)
+    K = (1392.1069298937407, 980.1759848618066, 604.3534182680304)  # fx, px, py (:62-70), k1 = k2 = 0
+    matches = np.stack([np.arange(len(uv1)), np.arange(len(uv1))], -1).astype(np.int64)
+    R, t, rows, ratio, E = verifier_ref.verify_cv2(uv1, uv2, matches, K, K, True, 0.5)
+    np.savez_compressed(OUT / "verifier_argoverse.npz", uv1=uv1, uv2=uv2, K=np.array(K), thr_px=0.5,
+                        euler_zyx_deg_gt=np.array([-0.37, 32.47, -0.42]), i1ti2_gt=np.array([0.21, -0.0024, 0.976]),
+                        euler_tol_deg=1.0, t_tol=0.01, R_cv=R, t_cv=t, rows_cv=rows, cv2_version=cv2.__version__)
+    e, tt = verifier_ref.pose_to_euler_zyx_and_i1ti2(R, t)
+    print(f"verifier argoverse: cv2 euler zyx {np.round(e, 2)}, i1ti2 {np.round(tt, 3)}, inliers {len(rows)}/20")
+
+
 def main():
     assert ref_modules.available(), "/root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -195,6 +219,7 @@ def main():
     golden_lightglue(feats)
     golden_superglue()
     golden_verifier()
+    golden_verifier_argoverse()
 
 
 if __name__ == "__main__":

@@ -78,6 +78,17 @@ def verify_cv2(
     return R, t.ravel(), rows, ratio, E
 
 
+def pose_to_euler_zyx_and_i1ti2(i2Ri1: np.ndarray, i2ti1: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """The quantities the reference's Argoverse known-answer test compares (tests/frontend/verifier/
+    test_verifier_argoverse.py:86-104): invert the relative pose, Euler angles 'zyx' in degrees of i1Ri2, and i1ti2."""
+    from scipy.spatial.transform import Rotation
+
+    i1Ri2 = np.asarray(i2Ri1, np.float64).T
+    t = np.asarray(i2ti1, np.float64).ravel()
+    i1ti2 = -i1Ri2 @ (t / np.linalg.norm(t))
+    return Rotation.from_matrix(i1Ri2).as_euler("zyx", degrees=True), i1ti2
+
+
 def _Rx(a):
     c, s = np.cos(a), np.sin(a)
     return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])

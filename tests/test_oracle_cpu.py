@@ -59,3 +59,17 @@ def test_verifier_oracle_vs_golden(golden_dir):
     assert verifier_ref.rot_angle_deg(R, Rc) < 1.0
     if cv2.__version__ == str(fx["cv2_version"]):
         assert np.array_equal(rows, fx["rows_cv"])
+
+
+def test_verifier_oracle_argoverse_known_answer(golden_dir):
+    """The reference's own known-answer vector for the verifier (tests/frontend/verifier/test_verifier_argoverse.py:
+    72-136): 20 hand-labelled correspondences, expected Euler angles +-1 deg and translation +-0.01 at 0.5 px."""
+    fx = np.load(golden_dir / "verifier_argoverse.npz")
+    uv1, uv2, K = fx["uv1"], fx["uv2"], tuple(fx["K"])
+    matches = np.stack([np.arange(len(uv1)), np.arange(len(uv1))], -1).astype(np.int64)
+    R, t, rows, ratio, _ = verifier_ref.verify_cv2(uv1, uv2, matches, K, K, True, float(fx["thr_px"]))
+    euler, i1ti2 = verifier_ref.pose_to_euler_zyx_and_i1ti2(R, t)
+    assert np.allclose(euler, fx["euler_zyx_deg_gt"], atol=float(fx["euler_tol_deg"])), euler
+    assert np.allclose(i1ti2, fx["i1ti2_gt"], atol=float(fx["t_tol"])), i1ti2
+    # test_5pt_algo_5correspondences (:119-136): must not crash; the wrapper's guard returns the failure tuple
+    assert verifier_ref.verify_cv2(uv1, uv2, matches[:5], K, K, True, 0.5)[0] is None

@@ -93,3 +93,21 @@ def test_contract_degenerate_and_repro():
     for _ in range(3):
         again = v2.verify(Keypoints(kpa), Keypoints(kpb), m2, cal2, cal2)
         assert np.array_equal(first[0].matrix(), again[0].matrix()) and np.array_equal(first[2], again[2])
+
+
+def test_argoverse_known_answer(golden_dir):
+    """The reference's known-answer test (tests/frontend/verifier/test_verifier_argoverse.py:72-136) on the CUDA verifier:
+    same labelled correspondences, intrinsics, threshold (0.5 px) and tolerances (+-1 deg, +-0.01)."""
+    fx = np.load(golden_dir / "verifier_argoverse.npz")
+    uv1, uv2, K = fx["uv1"], fx["uv2"], fx["K"]
+    cal = Cal3Bundler(K[0], 0, 0, K[1], K[2])
+    matches = np.stack([np.arange(len(uv1)), np.arange(len(uv1))], -1).astype(np.int64)
+    ver = B200Ransac(use_intrinsics_in_verification=True, estimation_threshold_px=float(fx["thr_px"]))
+    R, U, rows, ratio = ver.verify(Keypoints(uv1), Keypoints(uv2), matches, cal, cal)
+    assert R is not None
+    euler, i1ti2 = vr.pose_to_euler_zyx_and_i1ti2(R.matrix(), U.point3())
+    assert np.allclose(euler, fx["euler_zyx_deg_gt"], atol=float(fx["euler_tol_deg"])), euler
+    assert np.allclose(i1ti2, fx["i1ti2_gt"], atol=float(fx["t_tol"])), i1ti2
+    # 5 correspondences (:119-136): no crash, failure tuple
+    R5, U5, rows5, _ = ver.verify(Keypoints(uv1), Keypoints(uv2), matches[:5], cal, cal)
+    assert R5 is None and U5 is None and len(rows5) == 0
