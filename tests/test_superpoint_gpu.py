@@ -92,7 +92,7 @@ def test_rgb_input_and_plugin_contract(golden_dir, tmp_path):
     okp_m, _, _ = detect_and_describe(rgb, sd, 500, mask=mask)
     assert np.array_equal(kps_m.coordinates, okp_m) and len(desc_m) == len(okp_m)
     # run-to-run exactness (tests/repro_tests/.../test_detector_descriptor_reproducibility_base.py:31-36)
-    for _ in range(3):
+    for _ in range(10):
         k2, d2 = det.detect_and_describe(Image(rgb))
         assert k2 == kps and np.array_equal(d2, desc)
 
