@@ -222,10 +222,22 @@ __global__ void __launch_bounds__(256) k_lg_ln_gelu(LnJob j0, LnJob j1, const fl
 
 // two per-row heads in one pass: sigmoid(w1.x + b1) and sigmoid(w2.x + b2) (token confidence :84-94, matchability
 // :298-299).  Also raw logit of head 2 when zraw != null.  one warp per row.
-__global__ void __launch_bounds__(256) k_lg_rowheads(const float* __restrict__ x, int n, const float* __restrict__ w1,
-                                                      const float* __restrict__ b1, const float* __restrict__ w2,
-                                                      const float* __restrict__ b2, float* __restrict__ o1,
-                                                      float* __restrict__ o2, float* __restrict__ zraw) {
+struct HeadJob {  // one image's share of a two-image launch (blockIdx.y)
+  const float* x;
+  int n;
+  const float *w2, *b2;  // head 2 may be off for one image only (pruning threshold on the keypoint count)
+  float *o1, *o2, *zraw;
+};
+__global__ void __launch_bounds__(256) k_lg_rowheads(HeadJob j0, HeadJob j1, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1) {
+  const HeadJob& jb = blockIdx.y ? j1 : j0;
+  const float* __restrict__ x = jb.x;
+  const float* __restrict__ w2 = jb.w2;
+  const float* __restrict__ b2 = jb.b2;
+  float* __restrict__ o1 = jb.o1;
+  float* __restrict__ o2 = jb.o2;
+  float* __restrict__ zraw = jb.zraw;
+  const int n = jb.n;
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= n) return;
   const float4* row = reinterpret_cast<const float4*>(x + (size_t)r * 256);
@@ -254,9 +266,18 @@ __global__ void __launch_bounds__(256) k_lg_rowheads(const float* __restrict__ x
 // pruning decision + ordered compaction map for one image (single block):
 //   counters[0 + side] += #(conf < thr)            (check_if_stop numerator, lightglue.py:653-655)
 //   keep = matchability > (1 - width_conf) | conf <= thr   (:636-643); src[pos] = old index; counters[2 + side] = #kept
-__global__ void __launch_bounds__(1024) k_lg_prune_plan(const float* __restrict__ conf, const float* __restrict__ mat, int n,
-                                                         float thr, float keep_thr, int side, int* __restrict__ src,
-                                                         int* __restrict__ counters) {
+struct PruneJob {  // one image's share of a two-image launch (blockIdx.y = side)
+  const float *conf, *mat;
+  int n;
+  int* src;
+};
+__global__ void __launch_bounds__(1024) k_lg_prune_plan(PruneJob j0, PruneJob j1, float thr, float keep_thr, int* __restrict__ counters) {
+  const int side = blockIdx.y;
+  const PruneJob& jb = side ? j1 : j0;
+  const float* __restrict__ conf = jb.conf;
+  const float* __restrict__ mat = jb.mat;
+  int* __restrict__ src = jb.src;
+  const int n = jb.n;
   __shared__ int wtot[32];
   __shared__ int carry, unconf;
   if (threadIdx.x == 0) carry = 0, unconf = 0;
@@ -768,20 +789,27 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
     if (layer == LG_LAYERS - 1) break;
     if (!do_stop && !do_prune) continue;
     bool prune_side[2];
+    HeadJob hj[2];
+    PruneJob pj[2];
+    int mxn = 0;
     for (int i = 0; i < 2; ++i) {
       LgSide& sd = s->side[i];
       prune_side[i] = do_prune && sd.n > prm->prune_min_kpts;
-      const float* x = sd.x[sd.cur].as<float>();
-      B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, do_stop ? s->tw[layer].w : nullptr,
-                do_stop ? s->tw[layer].b : nullptr, prune_side[i] ? s->aw[layer].wm : nullptr,
-                prune_side[i] ? s->aw[layer].bm : nullptr, sd.conf.as<float>(), sd.mat.as<float>(), (float*)nullptr);
-      B2_CHECK_LAUNCH(ctx);
+      hj[i] = {sd.x[sd.cur].as<float>(), sd.n, prune_side[i] ? s->aw[layer].wm : nullptr, prune_side[i] ? s->aw[layer].bm : nullptr,
+               sd.conf.as<float>(), sd.mat.as<float>(), nullptr};
+      pj[i] = {sd.conf.as<float>(), sd.mat.as<float>(), sd.n, sd.src.as<int>()};
+      mxn = sd.n > mxn ? sd.n : mxn;
+    }
+    B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(mxn, 8), 2), 256, 0, st, hj[0], hj[1], do_stop ? s->tw[layer].w : nullptr,
+              do_stop ? s->tw[layer].b : nullptr);
+    B2_CHECK_LAUNCH(ctx);
+    for (int i = 0; i < 2; ++i) {
+      LgSide& sd = s->side[i];
       if (!do_stop) B2_CUDA(ctx, cudaMemsetAsync(sd.conf.p, 0, (size_t)sd.n * 4, st));  // confidences None -> never "<= thr"
       if (!prune_side[i]) B2_CUDA(ctx, cudaMemsetAsync(sd.mat.p, 0x7f, (size_t)sd.n * 4, st));  // huge positive: keep all
-      B2_LAUNCH(ctx, k_lg_prune_plan, 1, 1024, 0, st, sd.conf.as<float>(), sd.mat.as<float>(), sd.n,
-                do_stop ? s->thr[layer] : -1.0f, keep_thr, i, sd.src.as<int>(), counters);
-      B2_CHECK_LAUNCH(ctx);
     }
+    B2_LAUNCH(ctx, k_lg_prune_plan, dim3(1, 2), 1024, 0, st, pj[0], pj[1], do_stop ? s->thr[layer] : -1.0f, keep_thr, counters);
+    B2_CHECK_LAUNCH(ctx);
     B2_CUDA(ctx, cudaMemcpyAsync(hread, counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(ctx, cudaStreamSynchronize(st));
     if (do_stop) {
@@ -820,8 +848,10 @@ static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, 
     g.bias = aw.bf, g.scale = 0.25f;  // / 256 ** 0.25
     g.cf = sd.md.as<float>(), g.ldc = 256, g.cp = planes_of(sd.md, (size_t)sd.cap * 256), g.ldch = 256, g.M = sd.n, g.N = 256;
     if ((rc = lg_linear(ctx, st, s, g))) return rc;  // (the two images may stop with different sizes: separate launches)
-    B2_LAUNCH(ctx, k_lg_rowheads, cdiv(sd.n, 8), 256, 0, st, x, sd.n, (const float*)nullptr, (const float*)nullptr, aw.wm,
-              aw.bm, (float*)nullptr, (float*)nullptr, sd.ls.as<float>());
+    {
+      HeadJob hj1{x, sd.n, aw.wm, aw.bm, nullptr, nullptr, sd.ls.as<float>()};
+      B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(sd.n, 8), 1), 256, 0, st, hj1, hj1, (const float*)nullptr, (const float*)nullptr);
+    }
     B2_CHECK_LAUNCH(ctx);
   }
   B2_CUDA(ctx, s->sim.ensure((size_t)a.n * b.n * 4));
