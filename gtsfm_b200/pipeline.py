@@ -7,6 +7,7 @@ PyTorch is used for device buffers and the stream only; all arithmetic is libgts
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -29,7 +30,7 @@ class DeviceFeatures:
         return int(self.kp.shape[0])
 
 
-RESERVE_SMS_FOR_VERIFY = 8  # k_rs_hyp_E: 1000 hypotheses / 128 threads = 8 CTAs for ~1 ms
+RESERVE_SMS_FOR_VERIFY = int(os.environ.get("B2_RESERVE_SMS", "8"))  # k_rs_hyp_E keeps 16 x 64-thread CTAs busy for ~1 ms
 
 
 class DeviceFrontEnd:
