@@ -35,6 +35,7 @@ extern "C" void b2_destroy(b2_context* ctx) {
   rs_destroy(ctx);
   for (auto& b : ctx->stage_d) b.release();
   for (auto& b : ctx->stage_h) b.release();
+  for (auto& e : ctx->fcache) e.buf.release();
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
