@@ -37,7 +37,11 @@ LOOKAHEAD = 20
 NEW_FRAMES = 2
 PAIRS_PER_STEP = LOOKAHEAD * NEW_FRAMES
 THR_PX = 4.0
-DOMINANT_KERNEL = "k_flash"  # prefix: k_flash_tc (tcgen05) or k_flash_attn (forced SIMT)
+DOMINANT_KERNEL = "k_flash"  # prefix: k_flash_ps / k_flash_ts / k_flash_ws / k_flash_tc (tcgen05) or k_flash_attn (forced SIMT)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_flash_ps launch at this workload, from the `ncu --set full` capture
+# summarised in profiles/r01_flash_ps.txt (30.80 MB read + 0.68 MB written; the algorithmic minimum - q, k, v, o planes
+# of both images once - is 4 x 2 x 5000 x 256 x 4 B = 41 MB, i.e. K / V re-reads are served by L2)
+DOMINANT_KERNEL_DRAM_BYTES_PER_LAUNCH = 30.80e6 + 0.68e6
 CONFIG = {
     "workload": "SuperPoint+LightGlue+RANSAC-5pt, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] steady state, deep_front_end.yaml matcher)",
     "frame": [H, W], "max_keypoints": MAX_KP, "lookahead": LOOKAHEAD, "new_frames_per_step": NEW_FRAMES,
@@ -333,7 +337,8 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": traffic["h2d"], "d2h_bytes_per_step": traffic["d2h"]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": DOMINANT_KERNEL, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None, "peak_source": f"bf16_tflops_sustained ({peak_src})",
+                         "frac": achieved / tf_peak, "traffic": DOMINANT_KERNEL_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_unit": "bytes per launch (ncu, profiles/r01_flash_ps.txt)", "peak_source": f"bf16_tflops_sustained ({peak_src})",
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_launches / args.steps,
                          "kernel_share_of_step": k_ms / total_ms if total_ms else None},
             "work": {"matches_per_pair": stats["matches"] / max(1, stats["pairs"]), "inliers_per_pair": stats["inliers"] / max(1, stats["pairs"])},
