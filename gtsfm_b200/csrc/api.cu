@@ -52,6 +52,17 @@ extern "C" int b2_set_option(b2_context* ctx, const char* name, int64_t value) {
     ctx->reserve_sms = (int)value;
     return B2_OK;
   }
+  if (!strcmp(name, "feature_cache")) {  // 0: forget every cached upload and copy on every call; 1: cache (default)
+    if (value != 0 && value != 1) return b2_fail(ctx, B2_ERR_ARG, "feature_cache takes 0 or 1");
+    ctx->fcache_on = (int)value;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& e : ctx->fcache) {
+      e.buf.release();
+      e.host = nullptr, e.bytes = 0, e.sig = 0, e.stamp = 0;
+    }
+    return B2_OK;
+  }
   return b2_fail(ctx, B2_ERR_ARG, std::string("unknown option ") + name);
 }
 extern "C" uint64_t b2_h2d_bytes(const b2_context* ctx) { return ctx ? ctx->h2d_bytes : 0; }

@@ -46,7 +46,9 @@ uint64_t b2_launch_count(const b2_context* ctx);
 uint64_t b2_h2d_bytes(const b2_context* ctx);
 /* Tuning knobs.  "reserve_sms" = n: the persistent kernels (attention, GEMM) launch sm_count - n CTAs, leaving n SMs to
  * kernels of OTHER contexts / streams running concurrently (the batched front-end overlaps pair k's RANSAC with pair
- * k+1's matching; a one-CTA-per-SM kernel that finds an SM busy would otherwise wait for a whole CTA lifetime). */
+ * k+1's matching; a one-CTA-per-SM kernel that finds an SM busy would otherwise wait for a whole CTA lifetime).
+ * "feature_cache" = 0 | 1: drop every cached device copy of host feature arrays and (0) copy on every call / (1, default)
+ * cache again - for callers that rewrite feature arrays in place. */
 int b2_set_option(b2_context* ctx, const char* name, int64_t value);
 /* Live kernel timing for roofline reporting: CUDA events on the launching stream around every launch whose kernel name
  * starts with `kernel_prefix` (e.g. "k_flash_attn"), until b2_profile_stop, which returns the summed device time, the
