@@ -225,6 +225,52 @@ RM_HDN int upoly_real_roots(const double* p, int deg, double* roots, int max_roo
 // ---- 5-point essential-matrix solver (Nister 2004) -------------------------------------------------------------
 // x1, x2: 5 normalised correspondences; E_out: up to 10 solutions, row-major, x2^T E x1 = 0, Frobenius norm 1.
 RM_HDN int fivept_solve(const double (*x1)[2], const double (*x2)[2], double (*E_out)[9]) {
+#ifdef B2_FIVEPT_QR
+  // (opt-in, host-validated, not yet run on the GPU: see DESIGN.md section 8) null space of the 5 x 9 epipolar constraint
+  // matrix A by Householder QR of A^T (9 x 5): A^T = Q [R; 0], columns 5..8 of Q are an orthonormal basis of null(A).
+  // Five reflections instead of Jacobi sweeps on the 9 x 9 Gram matrix, which is half of the solver's arithmetic.
+  double basis[4][9];  // X, Y, Z, W
+  {
+    double a[9][5], hv[5][9], beta[5];
+    for (int p = 0; p < 5; ++p) {
+      const double q[9] = {x2[p][0] * x1[p][0], x2[p][0] * x1[p][1], x2[p][0], x2[p][1] * x1[p][0], x2[p][1] * x1[p][1],
+                           x2[p][1],            x1[p][0],            x1[p][1], 1.0};
+      for (int i = 0; i < 9; ++i) a[i][p] = q[i];
+    }
+    for (int j = 0; j < 5; ++j) {
+      double n2 = 0.0;
+      for (int i = j; i < 9; ++i) n2 += a[i][j] * a[i][j];
+      for (int i = 0; i < 9; ++i) hv[j][i] = 0.0;
+      beta[j] = 0.0;
+      if (!(n2 > 1e-300)) continue;  // rank-deficient sample: the reflection is the identity
+      const double alpha = a[j][j] > 0.0 ? -sqrt(n2) : sqrt(n2);
+      double v2 = 0.0;
+      for (int i = j; i < 9; ++i) {
+        hv[j][i] = a[i][j] - (i == j ? alpha : 0.0);
+        v2 += hv[j][i] * hv[j][i];
+      }
+      if (!(v2 > 1e-300)) continue;
+      beta[j] = 2.0 / v2;
+      for (int c = j; c < 5; ++c) {
+        double sdot = 0.0;
+        for (int i = j; i < 9; ++i) sdot += hv[j][i] * a[i][c];
+        sdot *= beta[j];
+        for (int i = j; i < 9; ++i) a[i][c] -= sdot * hv[j][i];
+      }
+    }
+    for (int k = 0; k < 4; ++k) {
+      double qv[9];
+      for (int i = 0; i < 9; ++i) qv[i] = (i == 5 + k) ? 1.0 : 0.0;
+      for (int j = 4; j >= 0; --j) {
+        double sdot = 0.0;
+        for (int i = j; i < 9; ++i) sdot += hv[j][i] * qv[i];
+        sdot *= beta[j];
+        for (int i = j; i < 9; ++i) qv[i] -= sdot * hv[j][i];
+      }
+      for (int i = 0; i < 9; ++i) basis[k][i] = qv[i];
+    }
+  }
+#else
   // null space of the 5 x 9 epipolar constraint matrix via the 4 smallest eigenvectors of Q^T Q
   double QtQ[81], Vn[81], wn[9];
   for (int i = 0; i < 81; ++i) QtQ[i] = 0.0;
@@ -247,6 +293,8 @@ RM_HDN int fivept_solve(const double (*x1)[2], const double (*x2)[2], double (*E
   double basis[4][9];  // X, Y, Z, W
   for (int k = 0; k < 4; ++k)
     for (int i = 0; i < 9; ++i) basis[k][i] = Vn[i * 9 + ord[k]];
+
+#endif
 
   // E(x,y,z) = x X + y Y + z Z + W, entries are degree-1 polynomials
   Poly E[9];

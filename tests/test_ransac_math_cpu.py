@@ -1,4 +1,5 @@
 """CPU suite: the fp64 two-view solvers the CUDA verifier compiles (gtsfm_b200/csrc/ransac_math.cuh) built for the host."""
+import re
 import shutil
 import subprocess
 from pathlib import Path
@@ -6,10 +7,26 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_fivept_svd_pose_host_build(tmp_path):
+def _build_and_run(tmp_path, flags):
     exe = tmp_path / "test_ransac_math"
     cxx = shutil.which("g++")
     assert cxx, "g++ is required"
-    subprocess.run([cxx, "-O2", "-std=c++17", "-x", "c++", str(ROOT / "tests/cpp/test_ransac_math.cpp"), "-o", str(exe)], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    subprocess.run([cxx, "-O2", "-std=c++17", *flags, "-x", "c++", str(ROOT / "tests/cpp/test_ransac_math.cpp"), "-o", str(exe)], check=True)
+    return subprocess.run([str(exe)], capture_output=True, text=True)
+
+
+def test_fivept_svd_pose_host_build(tmp_path):
+    r = _build_and_run(tmp_path, [])
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_fivept_qr_nullspace_variant(tmp_path):
+    """Opt-in `-DB2_FIVEPT_QR` (Householder-QR null space instead of the Jacobi eigen-solve: half the solver's arithmetic;
+    to be switched on after a GPU run).  Which solutions a 5-point solver loses depends on the null-space basis, so the
+    variant is held to the same statistical bar (>= 95 % of the seeded trials, no constraint / pose failure), not to the
+    shipped build's exact count."""
+    r = _build_and_run(tmp_path, ["-DB2_FIVEPT_QR"])
+    m = re.search(r"recovered in (\d+)/(\d+) trials, avg [\d.]+ solutions, worst err ([\d.e+-]+), constraint/pose fails (\d+)", r.stdout)
+    assert m, r.stdout + r.stderr
+    found, trials, worst, fails = int(m.group(1)), int(m.group(2)), float(m.group(3)), int(m.group(4))
+    assert found >= 0.95 * trials and fails == 0 and worst < 1e-8, r.stdout
