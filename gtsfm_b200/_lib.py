@@ -42,11 +42,12 @@ SIGNATURES = {
     "b2_debug_fetch": (C.c_int64, [_vp, C.c_char_p, _vp, C.c_int64]),
     "b2_debug_gemm_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "b2_superpoint_set_weights": (_i, [_vp, _vp, _sz]),
-    "b2_superpoint_detect_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _f, _i, _i, _vp, _vp, _i, _ip, _vp]),
-    "b2_superpoint_describe_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "b2_superpoint_detect_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _f, _i, _i, _vp, _vp, _i, _ip, C.POINTER(C.c_uint64), _vp]),
+    "b2_superpoint_describe_dev": (_i, [_vp, C.c_uint64, _vp, _i, _vp, _vp]),
+    "b2_superpoint_extract_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _f, _i, _i, _i, _vp, _vp, _vp, _ip, _vp]),
     "b2_topk_indices_dev": (_i, [_vp, _vp, _i, _i, _vp, _ip, _vp]),
-    "b2_superpoint_detect_host": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _ip]),
-    "b2_superpoint_describe_host": (_i, [_vp, _vp, _i, _vp]),
+    "b2_superpoint_detect_host": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _ip, C.POINTER(C.c_uint64)]),
+    "b2_superpoint_describe_host": (_i, [_vp, C.c_uint64, _vp, _i, _vp]),
     "b2_lightglue_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_lightglue_match_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip, _vp]),
     "b2_lightglue_match_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip]),

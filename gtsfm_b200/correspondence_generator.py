@@ -46,10 +46,15 @@ class B200CorrespondenceGenerator(_Base):
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         mine = D.shard_pairs(list(visibility_graph), rank, world)
         feats: Dict[int, DeviceFeatures] = {}
-        for idx in (range(len(images)) if world == 1 else D.images_needed(mine)):
+        # images of this rank's pairs, plus (so that every image gets keypoints) images no pair references: idx mod world
+        todo = set(range(len(images))) if world == 1 else set(D.images_needed(mine))
+        if world > 1:
+            paired = {i for p in visibility_graph for i in p}
+            todo |= {i for i in range(len(images)) if i not in paired and i % world == rank}
+        for idx in sorted(todo):
             img = images[idx].result() if hasattr(images[idx], "result") else images[idx]  # Dask Future or Image
             arr = img.value_array if hasattr(img, "value_array") else np.asarray(img)
-            feats[idx] = fe.detect(torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device))
+            feats[idx] = fe.detect(torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device), mask=getattr(img, "mask", None))
         local: Dict[Tuple[int, int], np.ndarray] = {}
         for (i1, i2) in mine:
             m, _ = fe.match(feats[i1], feats[i2])
@@ -63,5 +68,6 @@ class B200CorrespondenceGenerator(_Base):
             torch.distributed.all_gather_object(parts, {i: k for i, k in enumerate(keypoints) if k is not None})
             for part in parts:
                 for i, k in part.items():
-                    keypoints[i] = keypoints[i] or k
+                    if keypoints[i] is None:  # (an empty Keypoints is falsy: test identity, not truth)
+                        keypoints[i] = k
         return keypoints, matches

@@ -52,7 +52,11 @@ extern "C" int b2_set_option(b2_context* ctx, const char* name, int64_t value) {
     ctx->reserve_sms = (int)value;
     return B2_OK;
   }
-  if (!strcmp(name, "feature_cache")) {  // 0: forget every cached upload and copy on every call; 1: cache (default)
+  if (!strcmp(name, "force_simt")) {  // takes effect for models whose weights are set AFTER this call
+    ctx->force_simt = value ? 1 : 0;
+    return B2_OK;
+  }
+  if (!strcmp(name, "feature_cache")) {  // 0 (default): forget every cached upload and copy on every call; 1: cache
     if (value != 0 && value != 1) return b2_fail(ctx, B2_ERR_ARG, "feature_cache takes 0 or 1");
     ctx->fcache_on = (int)value;
     cudaSetDevice(ctx->device);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -84,8 +85,9 @@ struct RansacState;
 
 // Device copies of host feature arrays handed to the *_host matcher entry points.  GTSfM matches one image's (keypoints,
 // descriptors) against ~20-40 partners, always passing the same host arrays, so re-uploading 5 MB per image per pair is
-// most of the plugin path's PCIe traffic.  An entry is keyed by (host pointer, size) and validated by a signature over
-// ~600 sampled words, so a freed-and-reused address or rewritten array is re-uploaded.  B2_FEATURE_CACHE=0 disables it.
+// most of the plugin path's PCIe traffic.  OPT-IN (b2_set_option("feature_cache", 1) / B2_FEATURE_CACHE=1; the default copies
+// on every call like the reference does).  An entry is keyed by (host pointer, size) and validated by a hash over the FULL
+// contents, so a freed-and-reused address or an array edited in place anywhere is re-uploaded.
 struct FeatCacheEntry {
   const void* host = nullptr;
   size_t bytes = 0;
@@ -99,6 +101,7 @@ struct b2_context {
   int device = 0;
   int sm_count = 148;
   int reserve_sms = 0;  // SMs the persistent kernels of this context leave free (b2_set_option "reserve_sms")
+  int force_simt = -1;  // 1: models loaded afterwards run the exact-fp32 SIMT kernels (no tensor cores); -1 = B2_FORCE_SIMT env
   std::string err;
   std::mutex mu;
   uint64_t launches = 0;
@@ -117,6 +120,12 @@ struct b2_context {
   int fcache_on = -1;          // -1 = read B2_FEATURE_CACHE on first use
   uint64_t h2d_bytes = 0;      // bytes the *_host entry points that track them actually copied
 };
+
+inline bool b2_force_simt(const b2_context* ctx) {
+  if (ctx->force_simt >= 0) return ctx->force_simt != 0;
+  const char* e = getenv("B2_FORCE_SIMT");
+  return e && e[0] == '1';
+}
 
 inline int b2_fail(b2_context* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;

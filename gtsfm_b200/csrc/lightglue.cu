@@ -600,10 +600,7 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
-  {
-    const char* e = getenv("B2_FORCE_SIMT");
-    s->use_tc = !(e && e[0] == '1');
-  }
+  s->use_tc = !b2_force_simt(ctx);
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   B2_CUDA(ctx, s->hread.ensure(64));
   B2_CUDA(ctx, s->counters.ensure(64));
@@ -902,25 +899,38 @@ extern "C" int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const f
 }
 
 
-// 64-bit FNV-1a over ~600 words sampled across the array (head, tail and an even stride): the identity check of the
-// feature cache
+// Content hash of a host feature array: EVERY byte takes part (four interleaved 64-bit multiply-xorshift lanes over 8-byte
+// words, then the tail), so an in-place edit anywhere in the array changes the signature.  ~10 GB/s on one host core.
 static uint64_t b2_feat_signature(const void* host, size_t bytes) {
-  const uint32_t* w = static_cast<const uint32_t*>(host);
-  const size_t n = bytes / 4;
-  uint64_t h = 1469598103934665603ull ^ (uint64_t)bytes;
-  auto mix = [&](uint32_t v) { h = (h ^ v) * 1099511628211ull; };
-  const size_t edge = n < 32 ? n : 32;
-  for (size_t i = 0; i < edge; ++i) mix(w[i]), mix(w[n - 1 - i]);
-  const size_t step = n / 512 ? n / 512 : 1;
-  for (size_t i = 0; i < n; i += step) mix(w[i]);
-  return h;
+  const unsigned char* p = static_cast<const unsigned char*>(host);
+  const uint64_t K0 = 0x9E3779B97F4A7C15ull, K1 = 0xC2B2AE3D27D4EB4Full;
+  uint64_t h[4] = {K0 ^ bytes, K1 + bytes, K0 * 3 + bytes, K1 * 5 ^ bytes};
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      h[l] = (h[l] ^ w[l]) * K0;
+      h[l] ^= h[l] >> 29;
+    }
+  }
+  uint64_t tail = 0;
+  for (int sh = 0; i < bytes; ++i, sh += 8) {
+    tail ^= (uint64_t)p[i] << (sh & 63);
+    if ((sh & 63) == 56) h[0] = (h[0] ^ tail) * K1, h[0] ^= h[0] >> 31, tail = 0;
+  }
+  h[1] = (h[1] ^ tail) * K1;
+  uint64_t r = h[0];
+  for (int l = 1; l < 4; ++l) r = (r ^ (h[l] + K0 + (r << 6) + (r >> 2))) * K1, r ^= r >> 32;
+  return r;
 }
 // Device address of a host array: from the cache when the same (pointer, size, signature) was uploaded before, else
 // copied (into an LRU cache slot, or into `fallback` when the cache is off).
 static int b2_upload_cached(b2_context* ctx, const void* host, size_t bytes, DevBuf* fallback, cudaStream_t st, const void** dev) {
-  if (ctx->fcache_on < 0) {
+  if (ctx->fcache_on < 0) {  // OFF unless asked for: b2_set_option("feature_cache", 1) or B2_FEATURE_CACHE=1
     const char* e = getenv("B2_FEATURE_CACHE");
-    ctx->fcache_on = !(e && e[0] == '0');
+    ctx->fcache_on = (e && e[0] == '1') ? 1 : 0;
   }
   if (!ctx->fcache_on || bytes < 4) {
     B2_CUDA(ctx, fallback->ensure(bytes));

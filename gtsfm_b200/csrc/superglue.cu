@@ -338,8 +338,7 @@ extern "C" int b2_superglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-  const char* e = getenv("B2_FORCE_SIMT");
-  s->use_tc = !(e && e[0] == '1');
+  s->use_tc = !b2_force_simt(ctx);
   s->loaded = true;
   return B2_OK;
 }

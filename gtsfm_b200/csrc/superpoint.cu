@@ -39,13 +39,15 @@ struct SuperPointState {
   int H = 0, W = 0, Hc = 0, Wc = 0;
   int n_kp = 0;
   bool have_dense = false;
+  uint64_t map_token = 0;  // identifies the dense descriptor map a detect call left behind (checked by describe)
+  DevBuf sel_idx, sel_cnt; // device top-k selection of b2_superpoint_extract_dev
 };
 
 void sp_destroy(b2_context* ctx) {
   if (!ctx->sp) return;
   SuperPointState* s = ctx->sp;
   DevBuf* bufs[] = {&s->wblob, &s->wsplit_h, &s->wsplit_l, &s->errflag, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
-                    &s->rowcnt, &s->rowoff, &s->dense, &s->kpxy, &s->kpsc};
+                    &s->rowcnt, &s->rowoff, &s->dense, &s->kpxy, &s->kpsc, &s->sel_idx, &s->sel_cnt};
   for (DevBuf* b : bufs) b->release();
   delete s;
   ctx->sp = nullptr;
@@ -632,8 +634,7 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
     B2_CUDA(ctx, cudaDeviceSynchronize());
     tmp.release();
     B2_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
-    const char* e = getenv("B2_FORCE_SIMT");
-    s->use_tc = !(e && e[0] == '1') && tma_encoder() != nullptr;
+    s->use_tc = !b2_force_simt(ctx) && tma_encoder() != nullptr;
   }
   B2_CUDA(ctx, cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
   s->loaded = true;
@@ -642,7 +643,7 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
 
 static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, int channels, size_t pitch, float thr,
                           int nms_radius, int border, float* out_xy, float* out_score, int cap, int* out_n,
-                          cudaStream_t st) {
+                          cudaStream_t st, uint64_t* out_token = nullptr) {
   SuperPointState* s = ctx->sp;
   if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "superpoint weights not set");
   if (nms_radius != NR) return b2_fail(ctx, B2_ERR_ARG, "only nms_radius == 4 (the reference default) is built");
@@ -729,6 +730,8 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   }
   s->n_kp = n;
   s->have_dense = true;
+  s->map_token += 1;
+  if (out_token) *out_token = s->map_token;
   *out_n = n;
   ctx->debug["heat"] = {s->heat.as<float>(), (int64_t)H8 * W8};
   ctx->debug["nms"] = {s->nms.as<float>(), (int64_t)H8 * W8};
@@ -739,33 +742,35 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
 
 extern "C" int b2_superpoint_detect_dev(b2_context* ctx, const uint8_t* image, int H, int W, int channels, size_t pitch,
                                         float thr, int nms_radius, int border, float* out_xy, float* out_score, int cap,
-                                        int* out_n, void* stream) {
+                                        int* out_n, uint64_t* out_map_token, void* stream) {
   if (!ctx || !image || !out_xy || !out_score || !out_n || cap < 0) return B2_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   return sp_detect_impl(ctx, image, H, W, channels, pitch, thr, nms_radius, border, out_xy, out_score, cap, out_n,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, out_map_token);
 }
 
-static int sp_describe_impl(b2_context* ctx, const float* xy, int n, float* out_desc, cudaStream_t st) {
+static int sp_describe_impl(b2_context* ctx, uint64_t token, const float* xy, int n, float* out_desc, cudaStream_t st) {
   SuperPointState* s = ctx->sp;
   if (!s || !s->have_dense) return b2_fail(ctx, B2_ERR_STATE, "describe called before a successful detect");
+  if (token != s->map_token)
+    return b2_fail(ctx, B2_ERR_STATE, "stale feature-map token: another detect ran on this context since the token was issued");
   if (n == 0) return B2_OK;
   B2_LAUNCH(ctx, k_sample_desc, cdiv(n, 8), 256, 0, st, s->dense.as<float>(), s->Hc, s->Wc, xy, n, out_desc);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
 }
 
-extern "C" int b2_superpoint_describe_dev(b2_context* ctx, const float* xy, int n, float* out_desc, void* stream) {
+extern "C" int b2_superpoint_describe_dev(b2_context* ctx, uint64_t map_token, const float* xy, int n, float* out_desc, void* stream) {
   if (!ctx || n < 0 || (n > 0 && (!xy || !out_desc))) return B2_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  return sp_describe_impl(ctx, xy, n, out_desc, (cudaStream_t)stream);
+  return sp_describe_impl(ctx, map_token, xy, n, out_desc, (cudaStream_t)stream);
 }
 
 extern "C" int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, int H, int W, int channels, float thr,
                                          int nms_radius, int border, float* out_xy, float* out_score, int cap,
-                                         int* out_n) {
+                                         int* out_n, uint64_t* out_map_token) {
   if (!ctx || !image || !out_xy || !out_score || !out_n || cap < 0) return B2_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
@@ -776,7 +781,7 @@ extern "C" int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, 
   B2_CUDA(ctx, ctx->stage_d[2].ensure((size_t)cap * sizeof(float) + 16));
   B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[0].p, image, bytes, cudaMemcpyHostToDevice, st));
   int rc = sp_detect_impl(ctx, ctx->stage_d[0].as<uint8_t>(), H, W, channels, (size_t)W * channels, thr, nms_radius, border,
-                          ctx->stage_d[1].as<float>(), ctx->stage_d[2].as<float>(), cap, out_n, st);
+                          ctx->stage_d[1].as<float>(), ctx->stage_d[2].as<float>(), cap, out_n, st, out_map_token);
   if (rc) return rc;
   int n = *out_n < cap ? *out_n : cap;
   if (n > 0) {
@@ -787,7 +792,7 @@ extern "C" int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, 
   return B2_OK;
 }
 
-extern "C" int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int n, float* out_desc) {
+extern "C" int b2_superpoint_describe_host(b2_context* ctx, uint64_t map_token, const float* xy, int n, float* out_desc) {
   if (!ctx || n < 0 || (n > 0 && (!xy || !out_desc))) return B2_ERR_ARG;
   if (n == 0) return B2_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -796,7 +801,7 @@ extern "C" int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int
   B2_CUDA(ctx, ctx->stage_d[3].ensure((size_t)n * 2 * sizeof(float)));
   B2_CUDA(ctx, ctx->stage_d[4].ensure((size_t)n * 256 * sizeof(float)));
   B2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d[3].p, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = sp_describe_impl(ctx, ctx->stage_d[3].as<float>(), n, ctx->stage_d[4].as<float>(), st);
+  int rc = sp_describe_impl(ctx, map_token, ctx->stage_d[3].as<float>(), n, ctx->stage_d[4].as<float>(), st);
   if (rc) return rc;
   B2_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->stage_d[4].p, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
@@ -905,5 +910,53 @@ extern "C" int b2_topk_indices_dev(b2_context* ctx, const float* scores, int n, 
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaMemcpyAsync(out_k, ctx->stage_d[7].p, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2_CUDA(ctx, cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused device-resident extraction for the batched path: detect -> top-k (device radix select, row-major order kept) ->
+// gather -> describe in ONE call, one host synchronisation (the data-dependent count).  Replaces the host-side
+// Keypoints.get_top_k of the per-call plugin (gtsfm/common/keypoints.py:89-110) by its order-preserving device twin.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_kp(const float* __restrict__ xy, const float* __restrict__ sc, const int* __restrict__ idx,
+                                                    const int* __restrict__ cnt, float* __restrict__ oxy, float* __restrict__ osc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *cnt) return;
+  const int j = idx[i];
+  reinterpret_cast<float2*>(oxy)[i] = reinterpret_cast<const float2*>(xy)[j];
+  osc[i] = sc[j];
+}
+
+extern "C" int b2_superpoint_extract_dev(b2_context* ctx, const uint8_t* image, int H, int W, int channels, size_t pitch,
+                                         float thr, int nms_radius, int border, int max_keypoints, float* out_xy, float* out_score,
+                                         float* out_desc, int* out_n, void* stream) {
+  if (!ctx || !image || !out_xy || !out_score || !out_desc || !out_n || max_keypoints <= 0) return B2_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  SuperPointState* s = ctx->sp;
+  if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "superpoint weights not set");
+  const int Hc = H / 8, Wc = W / 8;
+  const int cap = (Hc * 8 / 5 + 1) * (Wc * 8 / 5 + 1);  // radius-4 maxima are >= 5 apart (Chebyshev)
+  B2_CUDA(ctx, s->kpsc.ensure((size_t)cap * 3 * sizeof(float)));
+  B2_CUDA(ctx, s->sel_idx.ensure((size_t)cap * sizeof(int)));
+  B2_CUDA(ctx, s->sel_cnt.ensure(16));
+  float* all_xy = s->kpsc.as<float>();
+  float* all_sc = all_xy + (size_t)cap * 2;
+  int n_all = 0;
+  uint64_t token = 0;
+  int rc = sp_detect_impl(ctx, image, H, W, channels, pitch, thr, nms_radius, border, all_xy, all_sc, cap, &n_all, st, &token);
+  if (rc) return rc;
+  n_all = n_all < cap ? n_all : cap;
+  *out_n = 0;
+  if (n_all == 0) return B2_OK;
+  const int k = n_all < max_keypoints ? n_all : max_keypoints;
+  B2_LAUNCH(ctx, k_topk_select, 1, 1024, 0, st, all_sc, n_all, max_keypoints, s->sel_idx.as<int>(), s->sel_cnt.as<int>());
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_gather_kp, cdiv(k, 256), 256, 0, st, all_xy, all_sc, s->sel_idx.as<int>(), s->sel_cnt.as<int>(), out_xy, out_score);
+  B2_CHECK_LAUNCH(ctx);
+  if ((rc = sp_describe_impl(ctx, token, out_xy, k, out_desc, st))) return rc;
+  *out_n = k;  // k_topk_select takes exactly min(n, k) entries
   return B2_OK;
 }

@@ -12,6 +12,7 @@ survive the host-side mask / top-k selection, instead of for every detection (id
 """
 from __future__ import annotations
 
+import threading
 from pathlib import Path
 from typing import Optional, Tuple, Union
 
@@ -35,6 +36,8 @@ class SuperPointEngine:
         self.ctx.check(self.ctx.lib.b2_superpoint_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superpoint_set_weights")
         self.h2d_bytes = 0  # bytes this engine copied host->device / device->host (bench.py's e2e accounting)
         self.d2h_bytes = 0
+        self.map_token = 0  # dense descriptor map left by the last detect (describe refuses any other)
+        self.lock = threading.RLock()  # detect + describe of one image form one critical section (shared plugin, threads)
 
     @staticmethod
     def capacity(h: int, w: int) -> int:
@@ -51,18 +54,23 @@ class SuperPointEngine:
         xy = np.empty((cap, 2), np.float32)
         sc = np.empty(cap, np.float32)
         n = _lib.C.c_int(0)
+        tok = _lib.C.c_uint64(0)
         rc = self.ctx.lib.b2_superpoint_detect_host(self.ctx.handle, _lib.ptr(img), h, w, ch, KEYPOINT_THRESHOLD, NMS_RADIUS,
-                                                    REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n))
+                                                    REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n), _lib.C.byref(tok))
         self.ctx.check(rc, "superpoint_detect")
+        self.map_token = tok.value
         k = min(n.value, cap)
         self.h2d_bytes += img.nbytes
         self.d2h_bytes += k * 12 + 4
         return xy[:k].copy(), sc[:k].copy()
 
-    def describe(self, xy: np.ndarray) -> np.ndarray:
+    def describe(self, xy: np.ndarray, map_token: Optional[int] = None) -> np.ndarray:
+        """Samples the dense map of the detect call that issued `map_token` (default: this engine's last detect); raises
+        B200Error if another image has been detected on the context in between."""
         xy = np.ascontiguousarray(xy, np.float32)
         out = np.empty((len(xy), DESC_DIM), np.float32)
-        self.ctx.check(self.ctx.lib.b2_superpoint_describe_host(self.ctx.handle, _lib.ptr(xy), len(xy), _lib.ptr(out)), "superpoint_describe")
+        tok = self.map_token if map_token is None else int(map_token)
+        self.ctx.check(self.ctx.lib.b2_superpoint_describe_host(self.ctx.handle, tok, _lib.ptr(xy), len(xy), _lib.ptr(out)), "superpoint_describe")
         self.h2d_bytes += xy.nbytes
         self.d2h_bytes += out.nbytes
         return out
@@ -99,12 +107,14 @@ class B200SuperPointDetectorDescriptor(DetectorDescriptorBase):
         arr = image.value_array
         if arr.ndim == 3 and arr.shape[2] not in (3, 4):
             raise ValueError("Input image dimensions are wrong")  # gtsfm/utils/images.py:39-40
-        xy, sc = eng.detect(arr)
-        keypoints = Keypoints(xy, scales=None, responses=sc)
-        if getattr(image, "mask", None) is not None:
-            keypoints, _ = keypoints.filter_by_mask(image.mask)
-        keypoints, _ = keypoints.get_top_k(self.max_keypoints)
-        if len(keypoints) == 0:
-            return keypoints, np.zeros((0, DESC_DIM), np.float32)
-        descriptors = eng.describe(np.asarray(keypoints.coordinates, np.float32))
+        with eng.lock:  # the dense map lives in the context between the two C calls
+            xy, sc = eng.detect(arr)
+            token = eng.map_token
+            keypoints = Keypoints(xy, scales=None, responses=sc)
+            if getattr(image, "mask", None) is not None:
+                keypoints, _ = keypoints.filter_by_mask(image.mask)
+            keypoints, _ = keypoints.get_top_k(self.max_keypoints)
+            if len(keypoints) == 0:
+                return keypoints, np.zeros((0, DESC_DIM), np.float32)
+            descriptors = eng.describe(np.asarray(keypoints.coordinates, np.float32), token)
         return keypoints, descriptors

@@ -7,6 +7,7 @@ PyTorch is used for device buffers and the stream only; all arithmetic is libgts
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -48,7 +49,6 @@ class DeviceFrontEnd:
         if lightglue_sd is not None:
             blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
             self.ctx.check(self.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
-        self._scratch: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         # verification runs on its own context + stream + host thread so that the (latency-bound, 16-CTA) RANSAC kernels of
         # pair p overlap the matcher kernels of pair p+1 (ctypes calls release the GIL)
         self._vctx: Optional[_lib.Context] = None
@@ -58,30 +58,46 @@ class DeviceFrontEnd:
     def _stream(self):
         return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def detect(self, image: torch.Tensor) -> DeviceFeatures:
-        """image: uint8 device tensor (H, W) or (H, W, 3|4), contiguous."""
+    def detect(self, image: torch.Tensor, mask: Optional[np.ndarray] = None) -> DeviceFeatures:
+        """image: uint8 device tensor (H, W) or (H, W, 3|4), contiguous.  One C call (detect -> device top-k -> describe): no
+        torch kernels on the path, and the dense map never outlives the call (interleaving images on one handle is safe).
+        `mask` (host (H, W) array, 1 = keep; gtsfm/common/keypoints.py:112-127) is applied BEFORE the top-k like the
+        reference wrapper does (gtsfm/.../superpoint.py:87-91); masked images take the two-call path."""
         assert image.dtype == torch.uint8 and image.is_cuda and image.is_contiguous()
         h, w = int(image.shape[0]), int(image.shape[1])
         ch = 1 if image.dim() == 2 else int(image.shape[2])
-        cap = SuperPointEngine.capacity(h, w)
-        if cap not in self._scratch:
-            self._scratch[cap] = (torch.empty((cap, 2), dtype=torch.float32, device=self.device),
-                                  torch.empty(cap, dtype=torch.float32, device=self.device),
-                                  torch.empty(cap, dtype=torch.int32, device=self.device))
-        xy, sc, idx = self._scratch[cap]
+        if mask is not None:
+            return self._detect_masked(image, h, w, ch, np.asarray(mask))
+        k = self.max_keypoints
+        kp = torch.empty((k, 2), dtype=torch.float32, device=self.device)
+        score = torch.empty(k, dtype=torch.float32, device=self.device)
+        desc = torch.empty((k, 256), dtype=torch.float32, device=self.device)
         n = _lib.C.c_int(0)
+        rc = self.lib.b2_superpoint_extract_dev(self.ctx.handle, _lib.ptr(image), h, w, ch, w * ch, KEYPOINT_THRESHOLD, NMS_RADIUS,
+                                                REMOVE_BORDERS, k, _lib.ptr(kp), _lib.ptr(score), _lib.ptr(desc), _lib.C.byref(n),
+                                                self._stream())
+        self.ctx.check(rc, "superpoint_extract_dev")
+        return DeviceFeatures(kp[: n.value], score[: n.value], desc[: n.value], (h, w))
+
+    def _detect_masked(self, image: torch.Tensor, h: int, w: int, ch: int, mask: np.ndarray) -> DeviceFeatures:
+        cap = SuperPointEngine.capacity(h, w)
+        xy = torch.empty((cap, 2), dtype=torch.float32, device=self.device)
+        sc = torch.empty(cap, dtype=torch.float32, device=self.device)
+        n, tok = _lib.C.c_int(0), _lib.C.c_uint64(0)
         rc = self.lib.b2_superpoint_detect_dev(self.ctx.handle, _lib.ptr(image), h, w, ch, w * ch, KEYPOINT_THRESHOLD, NMS_RADIUS,
-                                               REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n), self._stream())
+                                               REMOVE_BORDERS, _lib.ptr(xy), _lib.ptr(sc), cap, _lib.C.byref(n), _lib.C.byref(tok),
+                                               self._stream())
         self.ctx.check(rc, "superpoint_detect_dev")
         nk = min(n.value, cap)
-        k = _lib.C.c_int(0)
-        rc = self.lib.b2_topk_indices_dev(self.ctx.handle, _lib.ptr(sc), nk, self.max_keypoints, _lib.ptr(idx), _lib.C.byref(k), self._stream())
-        self.ctx.check(rc, "topk_indices_dev")
-        sel = idx[: k.value].long()
-        kp = xy[:nk].index_select(0, sel).contiguous()
-        score = sc[:nk].index_select(0, sel).contiguous()
-        desc = torch.empty((k.value, 256), dtype=torch.float32, device=self.device)
-        rc = self.lib.b2_superpoint_describe_dev(self.ctx.handle, _lib.ptr(kp), k.value, _lib.ptr(desc), self._stream())
+        hxy, hsc = xy[:nk].cpu().numpy(), sc[:nk].cpu().numpy()
+        r = np.round(hxy).astype(int)
+        keep = np.flatnonzero(mask[r[:, 1], r[:, 0]] == 1)
+        if len(keep) > self.max_keypoints:  # the k largest responses, ties by lower index, row-major order kept
+            keep = np.sort(keep[np.argsort(-hsc[keep], kind="stable")[: self.max_keypoints]])
+        kp = torch.from_numpy(np.ascontiguousarray(hxy[keep])).to(self.device)
+        score = torch.from_numpy(np.ascontiguousarray(hsc[keep])).to(self.device)
+        desc = torch.empty((len(keep), 256), dtype=torch.float32, device=self.device)
+        rc = self.lib.b2_superpoint_describe_dev(self.ctx.handle, tok.value, _lib.ptr(kp), len(keep), _lib.ptr(desc), self._stream())
         self.ctx.check(rc, "superpoint_describe_dev")
         return DeviceFeatures(kp, score, desc, (h, w))
 
@@ -118,14 +134,16 @@ class DeviceFrontEnd:
         ctx = ctx or self.ctx
         sptr = _lib.C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
         k = int(matches.shape[0])
-        mask = torch.zeros(max(k, 1), dtype=torch.uint8, device=self.device)
+        matches = matches.contiguous()  # kept alive in this frame until the C call has returned
+        with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+            mask = torch.zeros(max(k, 1), dtype=torch.uint8, device=self.device)  # zero-filled on the stream the kernels use
         if k < 6:  # opencv_verifier_base.py:70-79
             return None, None, None, 0, mask[:k]
         E, R, t = np.zeros(9), np.zeros(9), np.zeros(3)
         c1, c2 = np.asarray(cal1, np.float64), np.asarray(cal2, np.float64)
         n = _lib.C.c_int(0)
         prm = _lib.RansacParams(threshold_px / max(c1[0], c2[0]), RANSAC_SUCCESS_PROB, E_MAX_ITERS, seed)
-        rc = self.lib.b2_ransac_essential_dev(ctx.handle, _lib.ptr(a.kp), _lib.ptr(b.kp), _lib.ptr(matches.contiguous()), k, _lib.ptr(c1),
+        rc = self.lib.b2_ransac_essential_dev(ctx.handle, _lib.ptr(a.kp), _lib.ptr(b.kp), _lib.ptr(matches), k, _lib.ptr(c1),
                                               _lib.ptr(c2), _lib.C.byref(prm), _lib.ptr(E), _lib.ptr(mask), _lib.C.byref(n), _lib.ptr(R),
                                               _lib.ptr(t), sptr)
         ctx.check(rc, "ransac_essential_dev")

@@ -47,8 +47,12 @@ uint64_t b2_h2d_bytes(const b2_context* ctx);
 /* Tuning knobs.  "reserve_sms" = n: the persistent kernels (attention, GEMM) launch sm_count - n CTAs, leaving n SMs to
  * kernels of OTHER contexts / streams running concurrently (the batched front-end overlaps pair k's RANSAC with pair
  * k+1's matching; a one-CTA-per-SM kernel that finds an SM busy would otherwise wait for a whole CTA lifetime).
- * "feature_cache" = 0 | 1: drop every cached device copy of host feature arrays and (0) copy on every call / (1, default)
- * cache again - for callers that rewrite feature arrays in place. */
+ * "force_simt" = 0 | 1: models whose weights are set afterwards run the exact-fp32 SIMT kernels instead of the tcgen05
+ * split-fp16 ones (the on-device cross-check of the tensor-core path; tests only).
+ * "feature_cache" = 0 | 1: drop every cached device copy of host feature arrays and (0, default) copy on every call like the
+ * reference / (1) keep device copies keyed by (host pointer, size) and validated by a hash of the FULL contents, so arrays
+ * edited in place are re-sent.  Only pays off for callers that pass the same numpy buffers repeatedly (it does nothing for
+ * Dask tasks, which unpickle fresh arrays per call). */
 int b2_set_option(b2_context* ctx, const char* name, int64_t value);
 /* Live kernel timing for roofline reporting: CUDA events on the launching stream around every launch whose kernel name
  * starts with `kernel_prefix` (e.g. "k_flash_attn"), until b2_profile_stop, which returns the summed device time, the
@@ -72,13 +76,22 @@ int b2_superpoint_set_weights(b2_context* ctx, const float* host_blob, size_t n_
  * cv2's fixed-point COLOR_RGB2GRAY), row pitch in bytes.  Runs encoder + both heads + NMS + threshold + border
  * removal + ordered compaction.  Keypoints come out in row-major (y, then x) order like torch.nonzero.
  * out_xy: [cap][2] float (x, y); out_score: [cap] float; *out_n (HOST int) = number found (may exceed cap: only the
- * first cap are written).  Synchronises `stream` before returning (the count is data dependent). */
+ * first cap are written).  *out_map_token (HOST, may be NULL) identifies the dense descriptor map this call left in the
+ * context.  Synchronises `stream` before returning (the count is data dependent). */
 int b2_superpoint_detect_dev(b2_context* ctx, const uint8_t* image, int height, int width, int channels, size_t pitch,
                              float keypoint_threshold, int nms_radius, int border, float* out_xy, float* out_score,
-                             int cap, int* out_n, void* stream);
-/* Describe stage: bilinear-samples the dense descriptor map of the LAST detect call at `n` (x, y) positions and
- * L2-normalises.  out_desc: [n][256] float row-major.  Asynchronous on `stream`. */
-int b2_superpoint_describe_dev(b2_context* ctx, const float* xy, int n, float* out_desc, void* stream);
+                             int cap, int* out_n, uint64_t* out_map_token, void* stream);
+/* Describe stage: bilinear-samples the dense descriptor map identified by `map_token` at `n` (x, y) positions and
+ * L2-normalises.  Fails with a "stale feature-map token" error if another detect has run on the context since the token
+ * was issued (two images interleaved on one handle can therefore never get each other's descriptors).
+ * out_desc: [n][256] float row-major.  Asynchronous on `stream`. */
+int b2_superpoint_describe_dev(b2_context* ctx, uint64_t map_token, const float* xy, int n, float* out_desc, void* stream);
+/* Fused, self-contained extraction for the batched path: detect -> device top-k (the `max_keypoints` largest responses,
+ * ties by lower index, row-major order kept) -> describe, under one lock, one host synchronisation.  out_xy [max_keypoints][2],
+ * out_score [max_keypoints], out_desc [max_keypoints][256] are DEVICE buffers; *out_n (HOST) = keypoints written. */
+int b2_superpoint_extract_dev(b2_context* ctx, const uint8_t* image, int height, int width, int channels, size_t pitch,
+                              float keypoint_threshold, int nms_radius, int border, int max_keypoints, float* out_xy,
+                              float* out_score, float* out_desc, int* out_n, void* stream);
 /* Device top-k by score (k largest, ties broken by lower index), result kept in row-major order; writes the selected
  * indices (int32, ascending) and returns count in *out_k (HOST).  For the batched path; the per-call plugin uses the
  * reference's host argpartition to keep its index order. */
@@ -87,8 +100,8 @@ int b2_topk_indices_dev(b2_context* ctx, const float* scores, int n, int k, int3
 /* Host-pointer variants (H2D / D2H inside). */
 int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, int height, int width, int channels,
                               float keypoint_threshold, int nms_radius, int border, float* out_xy, float* out_score,
-                              int cap, int* out_n);
-int b2_superpoint_describe_host(b2_context* ctx, const float* xy, int n, float* out_desc);
+                              int cap, int* out_n, uint64_t* out_map_token);
+int b2_superpoint_describe_host(b2_context* ctx, uint64_t map_token, const float* xy, int n, float* out_desc);
 
 /* ---- LightGlue --------------------------------------------------------------------------------------------------- */
 /* `blob`: packed fp32 tensors in the order documented in gtsfm_b200/weights.py::LIGHTGLUE_ORDER (nn.Linear layout

@@ -211,15 +211,132 @@ def golden_verifier_argoverse():
     print(f"verifier argoverse: cv2 euler zyx {np.round(e, 2)}, i1ti2 {np.round(tt, 3)}, inliers {len(rows)}/20")
 
 
+# ---- round 2: the configurations the bench times and north_star names ------------------------------------------------
+def golden_lightglue_bench():
+    """(a) The BENCHED matcher configuration: 5000 x 5000 keypoints, 'bench' weights, 9 full layers, nothing pruned.
+    Inputs regenerate from a seed (bit-identical on the GPU box), so match indices must be EXACTLY the reference's."""
+    sd = syn.lightglue_state_dict(2, "bench")
+    model = ref_modules.ref_lightglue(sd)
+    for seed, n0, n1 in [(11, 5000, 5000), (12, 1024, 1024)]:
+        kp0, sc0, d0, kp1, sc1, d1, gt = syn.synthetic_features(seed, n0, n1)
+        m, stop, pr0, pr1, ms = run_ref_lightglue(model, kp0, d0, kp1, d1, (480, 640), (480, 640))
+        tr = {}
+        m2 = lightglue_ref.lightglue_match(kp0, d0, kp1, d1, sd, trace=tr)
+        assert np.array_equal(m, m2) and tr["stop"] == stop == 9, (len(m), len(m2), stop)
+        assert (tr["sizes"] == np.array([n0, n1])).all(), "bench weights must not prune"
+        np.savez_compressed(OUT / f"lightglue_bench_{seed}.npz", matches=m.astype(np.int32), stop=stop, sizes=tr["sizes"], mscores=ms,
+                            seed=seed, n0=n0, n1=n1, profile="bench")
+        print(f"lightglue bench seed {seed} ({n0},{n1}): K={len(m)} stop={stop}")
+    # the bench's own detect -> match chain: two frames of the bench sequence, wrapper top-k, 'bench' weights
+    frames, cal = syn.synthetic_sequence(8, 480, 640)
+    sp_sd = syn.superpoint_state_dict(0)
+    fa = superpoint_ref.detect_and_describe(frames[0], sp_sd, 5000)
+    fb = superpoint_ref.detect_and_describe(frames[5], sp_sd, 5000)
+    m, stop, *_ = run_ref_lightglue(model, fa[0], fa[2], fb[0], fb[2], (480, 640), (480, 640))
+    m2 = lightglue_ref.lightglue_match(fa[0], fa[2], fb[0], fb[2], sd)
+    assert np.array_equal(m, m2) and stop == 9
+    good = np.abs((fa[0][m[:, 0]] - fb[0][m[:, 1]]) - [40, 8]).max(1) < 0.5
+    np.savez_compressed(OUT / "pipeline_bench_seq_0_5.npz", matches=m.astype(np.int32), stop=stop, kp_a=fa[0].astype(np.int16),
+                        kp_b=fb[0].astype(np.int16), sc_a=fa[1], sc_b=fb[1], profile="bench", frames=np.array([0, 5]))
+    print(f"pipeline bench seq 0-5: Na={len(fa[0])} Nb={len(fb[0])} K={len(m)} geometrically right {int(good.sum())} stop={stop}")
+
+
+def golden_superpoint_mp1():
+    """(b) SuperPoint on a 1024 x 1024 frame (BASELINE configs[2], SURVEY cfg-B)."""
+    sd = syn.superpoint_state_dict(0)
+    model = ref_modules.ref_superpoint(sd)
+    gray = superpoint_ref.rgb_to_gray_u8(syn.synthetic_frame(2, 1024, 1024))
+    kp, sc, desc = run_ref_superpoint(model, gray)
+    kp2, sc2, desc2 = superpoint_ref.superpoint_forward(gray.astype(np.float32) / 255.0, sd)
+    assert np.array_equal(kp, kp2) and np.array_equal(sc, sc2)
+    err = float(np.abs(desc - desc2).max())
+    assert err <= 1e-6, err
+    sel = np.argpartition(-sc, 5000)[:5000] if len(kp) > 5000 else np.arange(len(kp))
+    stride = max(1, len(kp) // 256)
+    np.savez_compressed(OUT / "superpoint_mp1.npz", keypoints=kp.astype(np.int16), scores=sc, topk_sel=sel.astype(np.int32),
+                        desc_rows=np.arange(0, len(kp), stride, dtype=np.int32), desc=desc[::stride].copy(),
+                        desc_checksum=np.float64(desc.astype(np.float64).sum()), restatement_desc_err=np.float64(err),
+                        **{f"v_{k}": np.array(v) for k, v in versions().items()})
+    print(f"superpoint mp1: {gray.shape} N={len(kp)} restatement desc err {err:.2e}")
+
+
+def golden_superglue_large():
+    """(c) SuperGlue at 2048 and 5000 keypoints (Sinkhorn over 16.8 / 100 MB matrices)."""
+    sd = syn.superglue_state_dict(1, "sharp")
+    model = ref_modules.ref_superglue(sd, weights="outdoor", sinkhorn_iterations=20, descriptor_dim=256)
+    for seed, n0, n1 in [(12, 2048, 1900), (13, 5000, 5000)]:
+        kp0, sc0, d0, kp1, sc1, d1, gt = syn.synthetic_features(seed, n0, n1)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))[None]
+        data = {"keypoints0": t(kp0), "keypoints1": t(kp1), "descriptors0": t(d0.T), "descriptors1": t(d1.T),
+                "scores0": t(sc0), "scores1": t(sc1), "image0": torch.empty(1, 1, 480, 640), "image1": torch.empty(1, 1, 480, 640)}
+        with torch.no_grad():
+            pred = model(data)
+        m0 = pred["matches0"][0].numpy()
+        valid = m0 > -1
+        rows = np.hstack([np.arange(n0)[valid].reshape(-1, 1), np.arange(n1)[m0[valid]].reshape(-1, 1)]).astype(np.uint32)
+        rows2 = superglue_ref.superglue_match(kp0, sc0, d0, kp1, sc1, d1, (480, 640, 3), (480, 640, 3), sd)
+        assert np.array_equal(rows, rows2), f"superglue restatement != reference (seed {seed}): {len(rows)} vs {len(rows2)}"
+        np.savez_compressed(OUT / f"superglue_{seed}.npz", matches=rows, mscores=pred["matching_scores0"][0].numpy()[valid],
+                            seed=seed, n0=n0, n1=n1, profile="sharp")
+        print(f"superglue seed {seed} ({n0},{n1}): K={len(rows)}")
+
+
+def golden_lund_door():
+    """(d) BASELINE configs[0]: all 12 lund-door images (loader resize to short side 760) and the 66 exhaustive pairs through
+    SuperPoint (max 5000 keypoints, wrapper argpartition) -> LightGlue ('sharp' weights).  Stores the resized gray frames
+    (inputs that cannot be regenerated from a seed), every detection, the reference's top-k selection and per-pair matches."""
+    sp_sd = syn.superpoint_state_dict(0)
+    lg_sd = syn.lightglue_state_dict(2, "sharp")
+    sp_model = ref_modules.ref_superpoint(sp_sd)
+    lg_model = ref_modules.ref_lightglue(lg_sd)
+    img, feats = {}, []
+    for i in range(1, 13):
+        gray = load_lund_gray(i)
+        kp, sc, desc = run_ref_superpoint(sp_model, gray)
+        kp2, sc2, desc2 = superpoint_ref.superpoint_forward(gray.astype(np.float32) / 255.0, sp_sd)
+        assert np.array_equal(kp, kp2) and np.array_equal(sc, sc2) and np.abs(desc - desc2).max() <= 1e-6
+        sel = np.argpartition(-sc, 5000)[:5000] if len(kp) > 5000 else np.arange(len(kp))
+        img[f"gray_{i}"] = gray
+        img[f"kp_{i}"] = kp.astype(np.int16)
+        img[f"sc_{i}"] = sc
+        img[f"sel_{i}"] = sel.astype(np.int32)
+        img[f"desc_{i}"] = desc[sel][::20].copy()  # every 20th selected descriptor (250 rows)
+        feats.append((kp[sel], desc[sel], gray.shape))
+        print(f"lund image {i}: {gray.shape} N={len(kp)}")
+    np.savez_compressed(OUT / "lund_door_images.npz", **img, **{f"v_{k}": np.array(v) for k, v in versions().items()})
+    out = {}
+    n_matches = []
+    for a in range(12):
+        for b in range(a + 1, 12):
+            (kpa, da, sha), (kpb, db, shb) = feats[a], feats[b]
+            m, stop, *_ = run_ref_lightglue(lg_model, kpa, da, kpb, db, sha, shb)
+            if (a + b) % 7 == 0:  # restatement pinned on a subset (the rest is the unmodified reference alone)
+                assert np.array_equal(m, lightglue_ref.lightglue_match(kpa, da, kpb, db, lg_sd))
+            out[f"m_{a + 1}_{b + 1}"] = m.astype(np.int16)
+            out[f"stop_{a + 1}_{b + 1}"] = np.int32(stop)
+            n_matches.append(len(m))
+            print(f"lund pair {a + 1}-{b + 1}: K={len(m)} stop={stop}", flush=True)
+    np.savez_compressed(OUT / "lund_door_66pairs.npz", **out, profile="sharp")
+    print(f"lund door: 66 pairs, matches per pair min/median/max {min(n_matches)}/{int(np.median(n_matches))}/{max(n_matches)}")
+
+
 def main():
     assert ref_modules.available(), "/root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:  # e.g. `python -m oracle.make_golden lightglue_bench superpoint_mp1 superglue_large lund_door`
+        for name in sys.argv[1:]:
+            globals()[f"golden_{name}"]()
+        return
     feats = golden_superpoint()
     golden_lightglue(feats)
     golden_superglue()
     golden_verifier()
     golden_verifier_argoverse()
+    golden_lightglue_bench()
+    golden_superpoint_mp1()
+    golden_superglue_large()
+    golden_lund_door()
 
 
 if __name__ == "__main__":

@@ -20,7 +20,9 @@ def engine(ctx, profile):
     return LightGlueEngine(syn.lightglue_state_dict(2, profile), ctx=ctx)
 
 
-@pytest.mark.parametrize("tag", ["full_5", "full_6", "prune_7", "stop_8", "prune_9", "stop_10"])
+# bench_11 IS the configuration bench.py times: 5000 x 5000 keypoints, 'bench' weights, 9 full layers (79 key tiles x 160
+# attention items through the stream-K split / fix-up); bench_12 the same weights at 1024 keypoints
+@pytest.mark.parametrize("tag", ["full_5", "full_6", "prune_7", "stop_8", "prune_9", "stop_10", "bench_12", "bench_11"])
 def test_matches_equal_reference_fixture(b200_ctx, golden_dir, tag):
     fx = np.load(golden_dir / f"lightglue_{tag}.npz")
     kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
@@ -30,6 +32,44 @@ def test_matches_equal_reference_fixture(b200_ctx, golden_dir, tag):
     assert m.dtype == np.int64 and m.shape == fx["matches"].shape, f"{m.shape} vs {fx['matches'].shape}"
     assert np.array_equal(m, fx["matches"])
     np.testing.assert_allclose(sc, fx["mscores"], atol=2e-4)
+
+
+def test_bench_sequence_chain(b200_ctx, golden_dir):
+    """The bench's own detect -> top-k -> match chain (frames 0 and 5 of its synthetic sequence, 'bench' weights, full depth):
+    keypoints exact, then the reference-selected keypoints through describe + match give the reference's match rows."""
+    from gtsfm_b200.detector_descriptor import SuperPointEngine
+
+    fx = np.load(golden_dir / "pipeline_bench_seq_0_5.npz")
+    frames, _ = syn.synthetic_sequence(8, 480, 640)
+    sp = SuperPointEngine(syn.superpoint_state_dict(0), ctx=b200_ctx)
+    lg = engine(b200_ctx, "bench")
+    feats = []
+    for f, key in ((frames[0], "a"), (frames[5], "b")):
+        xy, sc = sp.detect(f)
+        ref = fx[f"kp_{key}"].astype(np.float32)
+        assert set(map(tuple, ref.tolist())) <= set(map(tuple, xy.tolist())), "reference-selected keypoints were not all detected"
+        feats.append((ref, sp.describe(ref)))
+    m = lg.match(feats[0][0], feats[0][1], feats[1][0], feats[1][1])
+    assert lg.last_stop == int(fx["stop"]) == 9
+    assert len(fx["matches"]) > 1000 and np.array_equal(m, fx["matches"].astype(np.int64))
+
+
+@pytest.mark.parametrize("tag", ["full_5", "prune_7", "stop_8"])
+def test_exact_fp32_simt_path(golden_dir, tag):
+    """The exact-fp32 SIMT kernels (set_option force_simt: no tensor cores, no planes) are the on-device cross-check of the
+    split-fp16 tcgen05 path; they must reproduce the same fixtures."""
+    from gtsfm_b200 import _lib
+
+    ctx = _lib.Context(0)
+    try:
+        ctx.set_option("force_simt", 1)
+        fx = np.load(golden_dir / f"lightglue_{tag}.npz")
+        kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
+        eng = LightGlueEngine(syn.lightglue_state_dict(2, str(fx["profile"])), ctx=ctx)
+        m = eng.match(kp0, d0, kp1, d1)
+        assert eng.last_stop == int(fx["stop"]) and np.array_equal(m, fx["matches"])
+    finally:
+        ctx.close()
 
 
 def test_final_descriptors_match_oracle(b200_ctx):
@@ -118,22 +158,41 @@ def test_plugin_contract(tmp_path, golden_dir):
         matcher.match(Keypoints(kp0), k1, d0, d1, (480, 640, 3), (480, 640, 3))
 
 
-def test_feature_cache_reuses_and_revalidates(b200_ctx, golden_dir):
-    """b2_lightglue_match_host keeps device copies of the host feature arrays (GTSfM matches one image against many
-    partners): a repeated call sends nothing, a rewritten array at the same address is detected and sent again."""
+def test_feature_cache_is_opt_in_and_hashes_everything(b200_ctx, golden_dir):
+    """b2_lightglue_match_host can keep device copies of host feature arrays (opt-in).  Off (default): every call uploads.
+    On: a repeated call sends nothing, and ANY in-place edit - here ONE float in the middle of a descriptor array - is
+    detected by the full-content hash and re-uploaded (a stale copy would silently change the matches)."""
     fx = np.load(golden_dir / "lightglue_full_5.npz")
     kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
     eng = engine(b200_ctx, str(fx["profile"]))
-    m1 = eng.match(kp0, d0, kp1, d1)
+    per_call = kp0.nbytes + d0.nbytes + kp1.nbytes + d1.nbytes
     sent = eng.h2d_bytes
-    m2 = eng.match(kp0, d0, kp1, d1)
-    assert np.array_equal(m1, fx["matches"]) and np.array_equal(m2, m1)
-    assert eng.h2d_bytes == sent, "second call with the same arrays must not upload anything"
-    # same buffers, new contents: swap the roles of the two images in place (shapes permitting) -> must re-upload
-    keep = d1.copy()
-    d1[:] = d1[::-1]
-    m3 = eng.match(kp0, d0, kp1, d1)
-    assert eng.h2d_bytes == sent + d1.nbytes, "a rewritten array must be sent again (and only that one)"
-    d1[:] = keep
-    m4 = eng.match(kp0, d0, kp1, d1)
-    assert np.array_equal(m4, m1) and not np.array_equal(m3, m1)
+    m0 = eng.match(kp0, d0, kp1, d1)
+    m0b = eng.match(kp0, d0, kp1, d1)
+    assert eng.h2d_bytes == sent + 2 * per_call, "cache off (default): both calls upload everything"
+    assert np.array_equal(m0, fx["matches"]) and np.array_equal(m0b, m0)
+    b200_ctx.set_option("feature_cache", 1)
+    try:
+        m1 = eng.match(kp0, d0, kp1, d1)
+        sent = eng.h2d_bytes
+        m2 = eng.match(kp0, d0, kp1, d1)
+        assert np.array_equal(m1, fx["matches"]) and np.array_equal(m2, m1)
+        assert eng.h2d_bytes == sent, "second call with the same arrays must not upload anything"
+        # one float in the middle of the array, at a position no sampled signature would visit
+        r, c = d1.shape[0] // 2 + 1, 131
+        keep = d1[r].copy()
+        d1[r, c] += 0.25
+        eng.match(kp0, d0, kp1, d1)
+        assert eng.h2d_bytes == sent + d1.nbytes, "an array edited in place must be sent again (and only that one)"
+        # a visible edit: replace one matched descriptor row by its negative -> that match must disappear
+        row = int(fx["matches"][len(fx["matches"]) // 2, 1])
+        d1[r] = keep
+        keep_row = d1[row].copy()
+        d1[row] = -d1[row]
+        m3 = eng.match(kp0, d0, kp1, d1)
+        assert row not in set(m3[:, 1].tolist()) and row in set(m1[:, 1].tolist())
+        d1[row] = keep_row
+        m4 = eng.match(kp0, d0, kp1, d1)
+        assert np.array_equal(m4, m1)
+    finally:
+        b200_ctx.set_option("feature_cache", 0)

@@ -23,7 +23,7 @@ def test_gray_conversion_matches_cv2():
     assert np.array_equal(superpoint_ref.rgb_to_gray_u8(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
 
 
-@pytest.mark.parametrize("tag", ["full_5", "prune_7", "stop_8", "prune_9"])
+@pytest.mark.parametrize("tag", ["full_5", "prune_7", "stop_8", "prune_9", "bench_12"])
 def test_lightglue_oracle_vs_golden(golden_dir, tag):
     fx = np.load(golden_dir / f"lightglue_{tag}.npz")
     kp0, _, d0, kp1, _, d1, _ = syn.synthetic_features(int(fx["seed"]), int(fx["n0"]), int(fx["n1"]))
@@ -33,11 +33,12 @@ def test_lightglue_oracle_vs_golden(golden_dir, tag):
     assert np.array_equal(tr["sizes"], fx["sizes"])
 
 
-@pytest.mark.parametrize("seed", [5, 9])
+@pytest.mark.parametrize("seed", [5, 9, 12])
 def test_superglue_oracle_vs_golden(golden_dir, seed):
     fx = np.load(golden_dir / f"superglue_{seed}.npz")
     kp0, sc0, d0, kp1, sc1, d1, _ = syn.synthetic_features(seed, int(fx["n0"]), int(fx["n1"]))
-    m = superglue_ref.superglue_match(kp0, sc0, d0, kp1, sc1, d1, (480, 640, 3), (480, 640, 3), syn.superglue_state_dict(1))
+    sd = syn.superglue_state_dict(1, str(fx["profile"]) if "profile" in fx else "full")
+    m = superglue_ref.superglue_match(kp0, sc0, d0, kp1, sc1, d1, (480, 640, 3), (480, 640, 3), sd)
     assert m.dtype == np.uint32 and np.array_equal(m, fx["matches"])
 
 
@@ -73,3 +74,21 @@ def test_verifier_oracle_argoverse_known_answer(golden_dir):
     assert np.allclose(i1ti2, fx["i1ti2_gt"], atol=float(fx["t_tol"])), i1ti2
     # test_5pt_algo_5correspondences (:119-136): must not crash; the wrapper's guard returns the failure tuple
     assert verifier_ref.verify_cv2(uv1, uv2, matches[:5], K, K, True, 0.5)[0] is None
+
+
+def test_lund_door_oracle_vs_golden(golden_dir):
+    """configs[0] fixture: the restatement reproduces the reference's detections on a lund-door frame and its match rows on
+    one of the 66 pairs (features = reference selection, descriptors recomputed by the oracle)."""
+    img = np.load(golden_dir / "lund_door_images.npz")
+    fx = np.load(golden_dir / "lund_door_66pairs.npz")
+    sp_sd = syn.superpoint_state_dict(0)
+    feats = {}
+    for i in (3, 11):
+        kp, sc, desc = superpoint_ref.superpoint_forward(img[f"gray_{i}"].astype(np.float32) / 255.0, sp_sd)
+        assert np.array_equal(kp, img[f"kp_{i}"].astype(np.float32))
+        np.testing.assert_allclose(sc, img[f"sc_{i}"], atol=1e-6)
+        sel = img[f"sel_{i}"]
+        assert np.abs(desc[sel][::20] - img[f"desc_{i}"]).max() < 1e-5
+        feats[i] = (kp[sel], desc[sel])
+    m = lightglue_ref.lightglue_match(feats[3][0], feats[3][1], feats[11][0], feats[11][1], syn.lightglue_state_dict(2, "sharp"))
+    assert np.array_equal(m, fx["m_3_11"].astype(np.int64))

@@ -26,12 +26,12 @@ def _gray(name, golden_dir):
     fx = np.load(golden_dir / f"superpoint_{name}.npz")
     if "gray" in fx:
         return fx["gray"], fx
-    frames = {"tiny": (0, 120, 160), "odd": (3, 203, 317), "vga": (1, 480, 640)}
+    frames = {"tiny": (0, 120, 160), "odd": (3, 203, 317), "vga": (1, 480, 640), "mp1": (2, 1024, 1024)}
     idx, h, w = frames[name]
     return rgb_to_gray_u8(syn.synthetic_frame(idx, h, w)), fx
 
 
-@pytest.mark.parametrize("name", ["tiny", "odd", "vga", "lund1", "lund2"])
+@pytest.mark.parametrize("name", ["tiny", "odd", "vga", "mp1", "lund1", "lund2"])  # mp1 = 1024 x 1024 (BASELINE configs[2])
 def test_detect_matches_reference_fixture(engine, golden_dir, name):
     gray, fx = _gray(name, golden_dir)
     xy, sc = engine.detect(gray)
@@ -100,3 +100,37 @@ def test_rgb_input_and_plugin_contract(golden_dir, tmp_path):
 def test_missing_weights_raise(tmp_path):
     with pytest.raises(FileNotFoundError):
         B200SuperPointDetectorDescriptor(weights_path=tmp_path / "nope.pth")
+
+
+def test_stale_map_token_is_refused(b200_ctx, golden_dir):
+    """Two images interleaved on one handle: describe with the first image's token after a second detect must fail loudly
+    instead of sampling the wrong dense map."""
+    from gtsfm_b200._lib import B200Error
+
+    eng = SuperPointEngine(syn.superpoint_state_dict(0), ctx=b200_ctx)
+    gray_a, _ = _gray("tiny", golden_dir)
+    gray_b, _ = _gray("odd", golden_dir)
+    xy_a, _ = eng.detect(gray_a)
+    tok_a = eng.map_token
+    d_a = eng.describe(xy_a[:16], tok_a)
+    eng.detect(gray_b)
+    with pytest.raises(B200Error, match="stale feature-map token"):
+        eng.describe(xy_a[:16], tok_a)
+    eng.detect(gray_a)
+    np.testing.assert_array_equal(eng.describe(xy_a[:16]), d_a)
+
+
+def test_exact_fp32_simt_path(golden_dir):
+    """SIMT fp32 convolutions (set_option force_simt) reproduce the reference keypoints as well."""
+    from gtsfm_b200 import _lib
+
+    ctx = _lib.Context(0)
+    try:
+        ctx.set_option("force_simt", 1)
+        eng = SuperPointEngine(syn.superpoint_state_dict(0), ctx=ctx)
+        gray, fx = _gray("odd", golden_dir)
+        xy, sc = eng.detect(gray)
+        assert np.array_equal(xy, fx["keypoints"].astype(np.float32))
+        assert np.abs(eng.describe(xy[fx["desc_rows"]]) - fx["desc"]).max() < DESC_TOL
+    finally:
+        ctx.close()

@@ -1,4 +1,5 @@
-"""GPU: the batched two-view seam (gtsfm_b200/two_view.py) returns, pair by pair, what the per-pair plugins return."""
+"""GPU: the batched two-view seam (gtsfm_b200/two_view.py) against the ORACLE (oracle/lightglue_ref + the cv2-driven
+oracle/verifier_ref), and against the per-pair plugins (same kernels, per-call API)."""
 import numpy as np
 import pytest
 import torch
@@ -38,6 +39,40 @@ def test_batch_equals_per_pair_plugins():
         np.testing.assert_allclose(r.i2Ui1.point3(), U.point3(), atol=1e-9)
         assert abs(r.inlier_ratio_est_model - ratio) < 1e-12
     assert n_ok >= 2, "the synthetic sequence should give verifiable pairs"
+
+
+def test_batch_matches_the_oracle():
+    """Putative matches must be the oracle's LightGlue rows bit for bit; pose / verified rows must agree with what
+    cv2.findEssentialMat(USAC_ACCURATE) + recoverPose return for them (OpenCV's RANSAC is not in /root/reference, so the
+    verified set is compared by IoU and the pose by angle: the tolerances of tests/test_verifier_gpu.py)."""
+    from oracle import lightglue_ref, verifier_ref
+
+    lg_sd = syn.lightglue_state_dict(2, "sharp")
+    fe = DeviceFrontEnd(syn.superpoint_state_dict(0), lg_sd, max_keypoints=1024)
+    frames, cal = syn.synthetic_sequence(4, 240, 320)
+    feats = {i: fe.detect(torch.from_numpy(f).cuda()) for i, f in enumerate(frames)}
+    pairs = [(0, 1), (0, 2), (1, 3)]
+    res = B200TwoViewBatch(fe, 4.0).run(feats, pairs, {i: cal for i in feats})
+    n_ok = 0
+    for (i1, i2) in pairs:
+        a, b = feats[i1], feats[i2]
+        kpa, kpb = a.kp.cpu().numpy(), b.kp.cpu().numpy()
+        m_ref = lightglue_ref.lightglue_match(kpa, a.desc.cpu().numpy(), kpb, b.desc.cpu().numpy(), lg_sd)
+        r = res[(i1, i2)]
+        assert r.num_putative == len(m_ref), f"pair {(i1, i2)}: {r.num_putative} putative matches vs oracle {len(m_ref)}"
+        m_gpu, _ = fe.match(a, b)
+        assert np.array_equal(m_gpu.cpu().numpy(), m_ref)
+        R, t, rows, ratio, E = verifier_ref.verify_cv2(kpa.astype(np.float64), kpb.astype(np.float64), m_ref, cal, cal, True, 4.0)
+        if R is None:
+            continue
+        n_ok += 1
+        assert r.i2Ri1 is not None
+        assert verifier_ref.rot_angle_deg(R, r.i2Ri1.matrix()) < 1.0
+        assert verifier_ref.dir_angle_deg(t, r.i2Ui1.point3()) < 5.0
+        mine, ref = set(map(tuple, r.v_corr_idxs.tolist())), set(map(tuple, rows.tolist()))
+        assert len(mine & ref) / max(1, len(mine | ref)) > 0.9, (len(mine), len(ref))
+        assert abs(r.inlier_ratio_est_model - ratio) < 0.08
+    assert n_ok >= 2
 
 
 def test_too_few_matches_is_the_failure_tuple():
