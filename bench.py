@@ -37,6 +37,7 @@ LOOKAHEAD = 20
 NEW_FRAMES = 2
 PAIRS_PER_STEP = LOOKAHEAD * NEW_FRAMES
 THR_PX = 4.0
+MATCH_BATCH = 8  # pairs per lock-step LightGlue batch (the library maximum)
 DOMINANT_KERNEL = "k_flash"  # prefix: k_flash_ps / k_flash_ts / k_flash_ws / k_flash_tc (tcgen05) or k_flash_attn (forced SIMT)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_flash_ps launch at this workload, from the `ncu --set full` capture
 # summarised in profiles/r01_flash_ps.txt (30.80 MB read + 0.68 MB written; the algorithmic minimum - q, k, v, o planes
@@ -226,11 +227,13 @@ def run_cuda(args):
         pending = []
         for j in range(NEW_FRAMES):
             f = fe.detect(frames_dev[c + j])
-            for prev in list(window):
-                m, _ = fe.match(prev, f)
-                pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next pair's matcher kernels
-                stats["matches"] += int(m.shape[0])
-                stats["pairs"] += 1
+            prevs = list(window)
+            for b0 in range(0, len(prevs), MATCH_BATCH):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
+                chunk = prevs[b0:b0 + MATCH_BATCH]
+                for prev, (m, _) in zip(chunk, fe.match_batch([(prev, f) for prev in chunk])):
+                    pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next batch's matcher kernels
+                    stats["matches"] += int(m.shape[0])
+                    stats["pairs"] += 1
             window.append(f)
         for fut in pending:  # every verification result is collected inside the step
             stats["inliers"] += fut.result()[3]

@@ -21,6 +21,11 @@ class LightGlueParams(C.Structure):
                 ("prune_min_kpts", C.c_int)]
 
 
+class LightGluePair(C.Structure):
+    _fields_ = [("kp0", C.c_void_p), ("desc0", C.c_void_p), ("n0", C.c_int), ("kp1", C.c_void_p), ("desc1", C.c_void_p), ("n1", C.c_int),
+                ("out_matches", C.c_void_p), ("out_scores", C.c_void_p), ("out_k", C.c_int), ("out_stop_layer", C.c_int)]
+
+
 class RansacParams(C.Structure):
     _fields_ = [("threshold", C.c_double), ("confidence", C.c_double), ("max_iters", C.c_int), ("seed", C.c_uint64)]
 
@@ -51,6 +56,7 @@ SIGNATURES = {
     "b2_lightglue_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_lightglue_match_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip, _vp]),
     "b2_lightglue_match_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip]),
+    "b2_lightglue_match_batched_dev": (_i, [_vp, C.POINTER(LightGluePair), _i, C.POINTER(LightGlueParams), _vp]),
     "b2_superglue_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_superglue_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _ip, _vp]),
     "b2_superglue_match_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _ip]),

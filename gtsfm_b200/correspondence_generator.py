@@ -56,9 +56,10 @@ class B200CorrespondenceGenerator(_Base):
             arr = img.value_array if hasattr(img, "value_array") else np.asarray(img)
             feats[idx] = fe.detect(torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device), mask=getattr(img, "mask", None))
         local: Dict[Tuple[int, int], np.ndarray] = {}
-        for (i1, i2) in mine:
-            m, _ = fe.match(feats[i1], feats[i2])
-            local[(i1, i2)] = m.cpu().numpy()
+        for c0 in range(0, len(mine), 8):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
+            chunk = mine[c0:c0 + 8]
+            for (i1, i2), (m, _) in zip(chunk, fe.match_batch([(feats[i1], feats[i2]) for i1, i2 in chunk])):
+                local[(i1, i2)] = m.cpu().numpy()
         matches = D.gather_pair_results(local)
         keypoints: List[Optional[Keypoints]] = [None] * len(images)
         for idx, f in feats.items():

@@ -52,6 +52,11 @@ extern "C" int b2_set_option(b2_context* ctx, const char* name, int64_t value) {
     ctx->reserve_sms = (int)value;
     return B2_OK;
   }
+  if (!strcmp(name, "lightglue_batch")) {  // pairs walked in lock-step by b2_lightglue_match_batched_dev (1..8; 0 = maximum)
+    if (value < 0 || value > 8) return b2_fail(ctx, B2_ERR_ARG, "lightglue_batch takes 0..8");
+    ctx->lg_batch = (int)value;
+    return B2_OK;
+  }
   if (!strcmp(name, "force_simt")) {  // takes effect for models whose weights are set AFTER this call
     ctx->force_simt = value ? 1 : 0;
     return B2_OK;

@@ -1,32 +1,77 @@
-// Persistent schedule of the TMEM-operand flash attention (attn_ts.cuh): same per-tile pipeline, different work split.
+// Persistent warp-specialised tcgen05 + TMA flash attention over a BATCH of problems, A operands in TMEM ("TS" MMAs),
+// split-fp16 operands (~fp32 accuracy).
 //
-// k_flash_ts launches (query-tile pair, head, problem, key split) CTAs: 640 CTAs of 20 key tiles each on 148 SMs = 4.3
-// waves with ~30 % of every CTA's life spent in prologue / epilogue (TMEM alloc, Q load, pipeline fill, partial store).
-// Here the whole launch is ONE linear space of (item, key tile) units - item = (problem, head, 256-query block) - cut
-// into equal contiguous ranges, one per SM ("stream-K" over the key dimension).  A CTA therefore runs 1-3 SEGMENTS
-// (item, key-tile range) back to back: TMEM stays allocated, the barriers keep running phase counters, the TMA producer
-// streams the next segment's K / V tiles while the current one drains, and the next segment's Q is stored and its first
-// logits issued before the softmax warps write the current segment's result.  A segment that covers its item completely
-// writes the normalised output planes; otherwise it writes an un-normalised partial (O, m, l), and the LAST segment of an
-// item to arrive (device-scope counter, stream-K "fix-up") combines the 2-3 partials in the same kernel.
+//   O[Nq][256] = softmax(scale * Q K^T) V per head; q / k / v arrive as fp16 hi / lo planes with UNSCALED lo
+//   (x ~= hi + lo, lo = fp16(x - hi)), the output leaves as hi / lo planes with the usual 2^11-scaled lo.
 //
-// TMEM layout, warp roles and hand-offs are those of attn_ts.cuh; all barrier parities are functions of running counters
-// (ring entry `ge`, tile `gt`, segment `seg`) that every role advances identically.
+// Why TMEM operands: a 128 x 64 x 16 SS-mode MMA reads 4 KB of A and 2 KB of B from shared memory per 32 tensor cycles
+// (192 B/clk > the 128 B/clk the SM's shared memory delivers).  Here Q lives in TMEM for a whole segment and P is written
+// back over its own logits in TMEM, so shared memory only carries the K / V tiles (B operands).
+//
+// One CTA (352 threads, one per SM) owns TWO 128-query tiles of one head at a time and streams 64-key tiles.
+// TMEM (512 columns; per query tile q at q * 256):
+//     [  0, 64) logits buffer 0: S (128 x 64 fp32), overwritten in place by P: hi = columns [0, 32), lo = [32, 64)
+//     [ 64,128) logits buffer 1                                                 (column c = keys 2c, 2c + 1 as half2)
+//     [128,192) O accumulator (128 x 64 fp32), accumulated by the tensor core across ALL key tiles of a segment
+//     [192,224) Q hi, [224,256) Q lo  (column c = dims 2c, 2c + 1)
+//   warp 8 lane 0 : TMA producer - K and V tiles through one 4-entry ring (128-byte swizzled, zero OOB fill)
+//   warps 9, 10   : MMA issuers of query tile 0 / 1 (warp-uniform issue, one elected lane; warp 9 also owns the TMEM
+//                   allocation).  Two issuers because a barrier wait costs the issuing warp 150-250 cycles and the
+//                   tcgen05 queue is shallow: while one warp waits for its P tile the other's MMAs keep the pipe busy.
+//                   Per key tile i, issuer q:
+//                     PV_q(i): O_q += Ph Vh + Ph Vl + Pl Vh   (A = P from TMEM, B = V MN-major)      12 tcgen05.mma
+//                     S_q(i+2) = Qh Kh^T + Qh Kl^T + Ql Kh^T  (A = Q from TMEM) into buffer i & 1    12 tcgen05.mma
+//                   the logits run two key tiles ahead of the softmax.
+//   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one thread per query row (= TMEM lane): tcgen05.ld S, base-2
+//                   online softmax with a LAZY reference maximum (O and l are only rescaled when the row maximum grew by
+//                   more than 2^8 - P then stays <= 256, exact in the hi / lo split - so O normally never leaves TMEM),
+//                   P = 2^(s - m) split to fp16 hi / lo and stored over S with tcgen05.st.
+// Hand-offs are mbarriers: TMA complete_tx (kv_full), tcgen05.commit (s_full, o_full, kv_empty) and 128-thread arrivals
+// (q_ready, p_full).
+//
+// Schedule ("stream-K" over the key dimension): the whole launch - every problem of the batch, i.e. the self- or
+// cross-attention of all images of up to 8 pairs - is ONE linear space of (item, key tile) units, item = (problem, head,
+// 256-query block), cut into equal contiguous ranges, one per SM.  A CTA therefore runs a few SEGMENTS (item, key-tile
+// range) back to back: TMEM stays allocated, the barriers keep running phase counters, the TMA producer streams the next
+// segment's K / V tiles while the current one drains, and the next segment's Q is stored and its first logits issued
+// before the softmax warps write the current segment's result.  A segment that covers its item completely writes the
+// normalised output planes; otherwise it writes an un-normalised partial (O, m, l), and the LAST segment of an item to
+// arrive (device-scope counter, stream-K "fix-up") combines the partials in the same kernel.  All barrier parities are
+// functions of running counters (ring entry `ge`, tile `gt`, segment `seg`) that every role advances identically.
 #pragma once
-#include "attn_ts.cuh"
+#include "tma.cuh"
+
+constexpr int AW_Q = 128, AW_KV = 64, AW_D = 64;
+constexpr int AW_KV_BYTES = AW_KV * AW_D * 2;  // 8 KB per plane
+constexpr int AS_NS = 4;                     // ring depth; entry e holds K tile e and V tile e - 2 (consumed together)
+constexpr int AS_HALF = 2 * AW_KV_BYTES;     // hi + lo plane of one 64 x 64 tile = 16 KB
+constexpr int AS_STAGE = 2 * AS_HALF;        // K part at +0, V part at +AS_HALF
+constexpr int AS_TILE_BYTES = AS_NS * AS_STAGE;
+constexpr size_t AS_SMEM = AS_TILE_BYTES + 1024 + 512;
+constexpr uint32_t AS_COL_O = 128, AS_COL_Q = 192;
+constexpr int AS_THREADS = 352;     // 8 softmax warps + TMA producer warp + 2 MMA issuer warps
+constexpr float AS_RESCALE = 8.0f;  // log2 of the largest P allowed before the reference maximum is refreshed
+constexpr int AP_MAXP = 16;         // problems per launch (2 images x 8 pairs)
+
+struct AttnPsMaps {
+  CUtensorMap kh[AP_MAXP], kl[AP_MAXP], vh[AP_MAXP], vl[AP_MAXP];  // per problem; 2-D views [4 * N rows][64] of the head-major planes
+};
 
 struct AttnPsProblem {
   const __half *Qh, *Ql;  // head-major planes [4][Nq][64]
   __half *Oh, *Ol;        // final output planes [Nq][256]
   int Nq, Nk;
   int qt, tiles;          // 256-query blocks, 64-key tiles
+  int w_end;              // running total of (item, key tile) units up to and including this problem
+  int item0;              // items (head x query block) of the problems before this one
 };
 struct AttnPsArgs {
-  AttnPsProblem p[2];
+  AttnPsProblem p[AP_MAXP];
+  int nprob;
   float* Opart;  // [item][max_splits][256][64] fp32, un-normalised
   float* ml;     // [item][max_splits][256][2]
   int* arrivals; // [item][2] zero on entry; counts the partials of (item, query tile) written so far, reset by the merger
-  int W0, W;     // units of problem 0, total units
+  int W;         // total units
   int quota;     // units per CTA
   int max_splits;
   float scale;
@@ -39,9 +84,10 @@ struct AttnPsSeg {
 // segment starting at unit w (clipped to w_end)
 __device__ __forceinline__ AttnPsSeg attn_ps_decode(const AttnPsArgs& a, int w, int w_end) {
   AttnPsSeg s;
-  s.z = w >= a.W0 ? 1 : 0;
+  s.z = 0;
+  while (s.z + 1 < a.nprob && w >= a.p[s.z].w_end) ++s.z;
   const AttnPsProblem& p = a.p[s.z];
-  const int base = s.z ? a.W0 : 0;
+  const int base = s.z ? a.p[s.z - 1].w_end : 0;
   const int wl = w - base;
   s.item = wl / p.tiles;
   s.tile0 = wl - s.item * p.tiles;
@@ -52,11 +98,11 @@ __device__ __forceinline__ AttnPsSeg attn_ps_decode(const AttnPsArgs& a, int w, 
   const int c_first = wi0 / a.quota;
   s.split = w / a.quota - c_first;
   s.nsplits = (wi1 - 1) / a.quota - c_first + 1;
-  s.itemg = (s.z ? a.p[0].qt * 4 : 0) + s.item;
+  s.itemg = p.item0 + s.item;
   return s;
 }
 
-static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_constant__ AttnTsMaps maps, AttnPsArgs args) {
+static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_constant__ AttnPsMaps maps, const __grid_constant__ AttnPsArgs args) {
   extern __shared__ unsigned char ap_raw[];
   const uint32_t raw = tc::smem_u32(ap_raw);
   const uint32_t smem0 = (raw + 1023u) & ~1023u;

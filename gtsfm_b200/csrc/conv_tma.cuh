@@ -13,8 +13,7 @@
 // convolution and / or fp32 for the SIMT head kernels.
 #pragma once
 #include "common.cuh"
-#include "gemm_tma.cuh"
-#include "tc.cuh"
+#include "tma.cuh"
 
 constexpr int CV_TH = 8, CV_TW = 16, CV_N = 64, CV_STAGES = 2;
 constexpr int CV_A_BYTES = 128 * 64 * 2;   // 16 KB per plane

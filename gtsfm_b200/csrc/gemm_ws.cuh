@@ -1,56 +1,85 @@
-// Persistent, warp-specialised tcgen05 + TMA split-fp16 "NT" GEMM:  C[M,N] = [A1 | A2][M,K] * B[N,K]^T  (both images).
+// Persistent, warp-specialised tcgen05 + TMA split-fp16 "NT" GEMM over a BATCH of problems that share one weight matrix:
+//     C_z[M_z, N] = [A1_z | A2_z][M_z, K] * B[N, K]^T        z = 0 .. nprob-1  (images of a batch of pairs)
+// or, with `b_per_problem`, one (A_z, B_z, N_z) triple per problem (the assignment similarity of every pair of a batch).
 //
-// Same arithmetic, operand layout and epilogue contract as gemm_tma.cuh (acc0 += Ah Bh ; acc1 += Ah Bl + Al Bh ;
-// result acc0 + acc1 * 2^-11).  What changes is the schedule.  The matcher's linears have K = 256 / 512 only, i.e. 4 - 8
-// K chunks per 128 x 64 output tile, so a one-tile-per-CTA kernel spends most of its life in prologue (barrier init,
-// TMEM alloc, first TMA round trip) and epilogue (TMEM -> registers -> global), with the tensor pipe idle (k_gemm_tma:
-// 99 TFLOP/s).  Here one CTA per SM walks tiles `blockIdx.x + i * gridDim.x`:
+// Arithmetic: every fp32 value travels as two fp16 planes, x ~= hi + lo * 2^-11 (the producing kernel's epilogue writes
+// them); three MMAs per K step,  acc0 += Ah Bh ; acc1 += Ah Bl + Al Bh ; result = acc0 + acc1 * 2^-11, both fp32
+// accumulators in TMEM.  The dropped Al * Bl term is 2^-22 relative.
+//
+// Schedule: one CTA per SM walks output tiles `blockIdx.x + i * gridDim.x` of the whole batch (problem-major, then row
+// tile, then column tile - concurrently running CTAs share the A row tile through L2):
 //   warp 0 (lane 0)  TMA producer: K chunks of consecutive tiles flow through one 3-stage ring without draining
-//   warp 1           TMEM allocator (256 columns = two accumulator sets) + MMA issuer (warp-uniform issue, tc.cuh)
-//   warps 2-9        epilogue: wait acc_full[set] -> tcgen05.ld -> release the set (acc_empty) -> shared-memory transpose
-//                    -> coalesced bias / scale / ReLU / residual -> fp32 and / or split planes.  Warp w owns TMEM lane
-//                    quarter w % 4 (rows) and column half (w - 2) / 4, so tile t's epilogue overlaps tile t + 1's MMAs.
+//   warp 1           TMEM allocator (512 columns = two accumulator sets of 2 x 128) + MMA issuer (warp-uniform issue, tc.cuh)
+//   warps 2-9        epilogue: wait acc_full[set] -> tcgen05.ld -> shared-memory transpose -> coalesced bias / scale / ReLU /
+//                    residual -> fp32 and / or split planes; the set is released (acc_empty) once its last column block is
+//                    in registers, so tile t's epilogue overlaps tile t + 1's MMAs.  Warp w owns TMEM lane quarter w % 4
+//                    (rows) and column half (w - 2) / 4.
+// Tile = 128 x 128: per 64-wide K chunk the tensor pipe needs 768 cycles for the three products, shared memory serves
+// 96 KB of operand reads + 64 KB of TMA writes; the 128 x 64 tile of round 1 moved 1.5x the bytes per FLOP.
 #pragma once
-#include "gemm_tma.cuh"
+#include "tma.cuh"
 
-constexpr int GW_STAGES = 4;
+constexpr int GW_MAXP = 16;  // problems per launch (2 images x 8 pairs)
+constexpr int GW_M = 128, GW_N = 128, GW_K = 64;
+constexpr int GW_A_BYTES = GW_M * GW_K * 2;  // 16 KB per plane
+constexpr int GW_B_BYTES = GW_N * GW_K * 2;  // 16 KB per plane
+constexpr int GW_STAGE_BYTES = 2 * GW_A_BYTES + 2 * GW_B_BYTES;  // 64 KB
+constexpr int GW_STAGES = 3;
 constexpr int GW_THREADS = 320;
 constexpr int GW_SCRATCH = 8 * 32 * 33 * 4;  // one 32 x 33 fp32 transpose pad per epilogue warp
-constexpr size_t GW_SMEM = GW_STAGES * TM_STAGE_BYTES + GW_SCRATCH + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr size_t GW_SMEM = GW_STAGES * GW_STAGE_BYTES + GW_SCRATCH + 1024 /*align slack*/ + 256 /*barriers*/;
 
+struct GemmProblem {
+  const float* resid;  // [M][ldr] fp32 or null, added after bias / scale
+  float* C;            // optional fp32 output, row-major [M][ldc]
+  __half *Ch, *Cl;     // optional split output planes
+  int M, N, ldc;
+  int tiles_n;   // ceil(N / 128)
+  int tile_end;  // running total of tiles up to and including this problem
+};
+struct GemmWsMaps {  // 128-byte TMA descriptors, passed as a __grid_constant__ kernel parameter
+  CUtensorMap a1h[GW_MAXP], a1l[GW_MAXP];  // per problem: first K segment
+  CUtensorMap a2h[GW_MAXP], a2l[GW_MAXP];  // optional second K segment (torch.cat([x, msg], -1) without the concat)
+  CUtensorMap bh[GW_MAXP], bl[GW_MAXP];    // [0] when every problem shares the weight matrix
+};
 struct GemmWsArgs {
-  GemmTmaArgs g;
-  int tiles_n;   // ceil(N / 64)
-  int tiles_m0;  // row tiles of problem 0; problem 1 follows
-  int tiles;     // total
+  GemmProblem p[GW_MAXP];
+  int nprob, tiles;
+  int K1, K2;
+  int b_per_problem;
+  const float* bias;  // [N] or null
+  int ldr;
+  float scale;
+  int ldch;        // row-major leading dimension of Ch / Cl (ignored when head_major)
+  int head_major;  // 1: Ch / Cl (and C) are written as [N/64][M][64] (attention head layout)
+  int relu;        // max(., 0) after bias / scale, before the residual
+  int lo_unscaled; // split outputs keep lo = fp16(x - hi) (attention operands)
+  int* err_flag;   // set to 1 if an mbarrier wait timed out (pipeline bug): results are then invalid
 };
 
-static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_constant__ GemmTmaMaps maps, GemmWsArgs w) {
+static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_constant__ GemmWsMaps maps, const __grid_constant__ GemmWsArgs g) {
   extern __shared__ unsigned char gw_raw[];
   const uint32_t raw = tc::smem_u32(gw_raw);
   const uint32_t smem0 = (raw + 1023u) & ~1023u;
   unsigned char* sm = gw_raw + (smem0 - raw);
-  float* scratch_all = reinterpret_cast<float*>(sm + GW_STAGES * TM_STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + GW_STAGES * TM_STAGE_BYTES + GW_SCRATCH);
+  float* scratch_all = reinterpret_cast<float*>(sm + GW_STAGES * GW_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + GW_STAGES * GW_STAGE_BYTES + GW_SCRATCH);
   uint64_t* empty = full + GW_STAGES;
   uint64_t* acc_full = empty + GW_STAGES;  // [2] all MMAs of the tile in accumulator set b have completed
   uint64_t* acc_empty = acc_full + 2;      // [2] the 8 epilogue warps have read set b out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const GemmTmaArgs& g = w.g;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int nk = (g.K1 + g.K2) / TM_K;
+  const int nk = (g.K1 + g.K2) / GW_K;
 
   if (t == 0) {
     for (int s = 0; s < GW_STAGES; ++s) tc::mbar_init(&full[s], 1), tc::mbar_init(&empty[s], 1);
     for (int b = 0; b < 2; ++b) tc::mbar_init(&acc_full[b], 1), tc::mbar_init(&acc_empty[b], 8);
     tc::fence_mbar_init();
-    tc::tma_prefetch_desc(&maps.a1h[0]);
-    tc::tma_prefetch_desc(&maps.a1l[0]);
-    tc::tma_prefetch_desc(&maps.bh);
-    tc::tma_prefetch_desc(&maps.bl);
+    tc::tma_prefetch_desc(&maps.bh[0]);
+    tc::tma_prefetch_desc(&maps.bl[0]);
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 4 * TM_N);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -58,60 +87,63 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
   bool ok = true;
 
   auto decode = [&](int tile, int& z, int& m0, int& n0) {
-    const int mt = tile / w.tiles_n;
-    n0 = (tile - mt * w.tiles_n) * TM_N;
-    z = mt >= w.tiles_m0 ? 1 : 0;
-    m0 = (mt - z * w.tiles_m0) * TM_M;
+    z = 0;
+    while (z + 1 < g.nprob && tile >= g.p[z].tile_end) ++z;
+    const int local = tile - (z ? g.p[z - 1].tile_end : 0);
+    const int mt = local / g.p[z].tiles_n;
+    n0 = (local - mt * g.p[z].tiles_n) * GW_N;
+    m0 = mt * GW_M;
   };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int gk = 0;
-      for (int tile = blockIdx.x; tile < w.tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
         int z, m0, n0;
         decode(tile, z, m0, n0);
+        const int zb = g.b_per_problem ? z : 0;
         for (int kc = 0; kc < nk; ++kc, ++gk) {
           const int s = gk % GW_STAGES;
           if (gk >= GW_STAGES) ok = tc::mbar_wait(&empty[s], ((gk / GW_STAGES) - 1) & 1) && ok;
-          const int k0 = kc * TM_K;
+          const int k0 = kc * GW_K;
           const bool seg2 = k0 >= g.K1;
           const CUtensorMap* ah = seg2 ? &maps.a2h[z] : &maps.a1h[z];
           const CUtensorMap* al = seg2 ? &maps.a2l[z] : &maps.a1l[z];
           const int ka = seg2 ? k0 - g.K1 : k0;
-          const uint32_t sA = smem0 + s * TM_STAGE_BYTES, sB = sA + 2 * TM_A_BYTES;
-          tc::mbar_expect_tx(&full[s], TM_STAGE_BYTES);
+          const uint32_t sA = smem0 + s * GW_STAGE_BYTES, sB = sA + 2 * GW_A_BYTES;
+          tc::mbar_expect_tx(&full[s], GW_STAGE_BYTES);
           tc::tma_load_2d(sA, ah, &full[s], ka, m0);
-          tc::tma_load_2d(sA + TM_A_BYTES, al, &full[s], ka, m0);
-          tc::tma_load_2d(sB, &maps.bh, &full[s], k0, n0);
-          tc::tma_load_2d(sB + TM_B_BYTES, &maps.bl, &full[s], k0, n0);
+          tc::tma_load_2d(sA + GW_A_BYTES, al, &full[s], ka, m0);
+          tc::tma_load_2d(sB, &maps.bh[zb], &full[s], k0, n0);
+          tc::tma_load_2d(sB + GW_B_BYTES, &maps.bl[zb], &full[s], k0, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp, one elected lane issues) =====
-    const uint32_t idesc = tc::idesc_f16(TM_M, TM_N);
+    const uint32_t idesc = tc::idesc_f16(GW_M, GW_N);
     int gk = 0, it = 0;
     bool hint = false;  // next stage already seen full by a pre-poll
-    for (int tile = blockIdx.x; tile < w.tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       if (it >= 2) ok = tc::mbar_wait(&acc_empty[b], ((it >> 1) - 1) & 1) && ok;
-      const uint32_t acc = tmem + b * (2 * TM_N);
+      const uint32_t acc = tmem + b * (2 * GW_N);
       for (int kc = 0; kc < nk; ++kc, ++gk) {
         const int s = gk % GW_STAGES;
         if (!hint) ok = tc::mbar_wait(&full[s], (gk / GW_STAGES) & 1) && ok;
         __syncwarp();
         tc::fence_after_sync();
         hint = tc::mbar_test(&full[(gk + 1) % GW_STAGES], ((gk + 1) / GW_STAGES) & 1);
-        const uint32_t aH = smem0 + s * TM_STAGE_BYTES, aL = aH + TM_A_BYTES, bH = aH + 2 * TM_A_BYTES, bL = bH + TM_B_BYTES;
+        const uint32_t aH = smem0 + s * GW_STAGE_BYTES, aL = aH + GW_A_BYTES, bH = aH + 2 * GW_A_BYTES, bL = bH + GW_B_BYTES;
         const uint64_t dAh = tc::smem_desc_sw128(aH), dAl = tc::smem_desc_sw128(aL), dBh = tc::smem_desc_sw128(bH), dBl = tc::smem_desc_sw128(bL);
 #pragma unroll
-        for (int ks = 0; ks < TM_K / 16; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);
+        for (int ks = 0; ks < GW_K / 16; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the start-address field
           const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
           tc::umma_f16_w(acc, dAh + adv, dBh + adv, idesc, first);         // acc0 (+)= Ah Bh
-          tc::umma_f16_w(acc + TM_N, dAh + adv, dBl + adv, idesc, first);  // acc1 (+)= Ah Bl
-          tc::umma_f16_w(acc + TM_N, dAl + adv, dBh + adv, idesc, 1u);     // acc1  += Al Bh
+          tc::umma_f16_w(acc + GW_N, dAh + adv, dBl + adv, idesc, first);  // acc1 (+)= Ah Bl
+          tc::umma_f16_w(acc + GW_N, dAl + adv, dBh + adv, idesc, 1u);     // acc1  += Al Bh
         }
         tc::umma_commit_w(&empty[s]);
       }
@@ -121,55 +153,75 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
     // ===== epilogue warps =====
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int cc = ew >> 2;                  // 32-column half of the tile
+    const int chalf = ew >> 2;               // 64-column half of the tile
     float* scratch = scratch_all + ew * (32 * 33);
     const float scale = g.scale;
     const int relu = g.relu;
     int it = 0;
-    for (int tile = blockIdx.x; tile < w.tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
       int z, m0, n0;
       decode(tile, z, m0, n0);
-      const GemmTcProblem& pb = g.p[z];
-      const int M = pb.M;
+      const GemmProblem& pb = g.p[z];
+      const int M = pb.M, N = pb.N;
       const int b = it & 1;
       ok = tc::mbar_wait(&acc_full[b], (it >> 1) & 1) && ok;
       tc::fence_after_sync();
-      const uint32_t lane_base = tmem + b * (2 * TM_N) + ((uint32_t)(quarter * 32) << 16);
-      {
-        float a0[32], a1[32];
-        tc::tmem_ld32(lane_base + cc * 32, a0);
-        tc::tmem_ld32(lane_base + TM_N + cc * 32, a1);
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&acc_empty[b]);  // this warp's share of the set is in registers
-#pragma unroll
-        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = fmaf(a1[j], tc::LO_INV, a0[j]);
-      }
-      __syncwarp();
+      const uint32_t lane_base = tmem + b * (2 * GW_N) + ((uint32_t)(quarter * 32) << 16);
       const int mw = m0 + quarter * 32;
       const int rows = min(32, M - mw);
-      const int n = n0 + cc * 32 + lane;
-      if (n < g.N && rows > 0) {
-        const float bn = g.bias ? g.bias[n] : 0.f;
-        const size_t off_h = ((size_t)(n >> 6) * M + mw) * 64 + (n & 63);
-        const size_t off_c = g.head_major ? off_h : (size_t)mw * g.ldc + n;
-        const size_t off_s = g.head_major ? off_h : (size_t)mw * g.ldch + n;
-        const int str_c = g.head_major ? 64 : g.ldc, str_s = g.head_major ? 64 : g.ldch;
-        const float* rp = pb.resid ? pb.resid + (size_t)mw * g.ldr + n : nullptr;
-        float* cp = pb.C ? pb.C + off_c : nullptr;
-        __half* hp = pb.Ch ? pb.Ch + off_s : nullptr;
-        __half* lp = pb.Ch ? pb.Cl + off_s : nullptr;
-        const float* sp = scratch + lane;
-        if (rp) {
-          float rv[32];
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = chalf * 64 + cc * 32;
+        {
+          float a0[32], a1[32];
+          tc::tmem_ld32(lane_base + c0, a0);
+          tc::tmem_ld32(lane_base + GW_N + c0, a1);
+          if (cc == 1) {  // this warp's share of the set is in registers
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+          }
 #pragma unroll
-          for (int r = 0; r < 32; ++r) rv[r] = r < rows ? rp[(size_t)r * g.ldr] : 0.f;
+          for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = fmaf(a1[j], tc::LO_INV, a0[j]);
+        }
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        if (n < N && rows > 0) {
+          const float bn = g.bias ? g.bias[n] : 0.f;
+          const size_t off_h = ((size_t)(n >> 6) * M + mw) * 64 + (n & 63);
+          const size_t off_c = g.head_major ? off_h : (size_t)mw * pb.ldc + n;
+          const size_t off_s = g.head_major ? off_h : (size_t)mw * g.ldch + n;
+          const int str_c = g.head_major ? 64 : pb.ldc, str_s = g.head_major ? 64 : g.ldch;
+          const float* rp = pb.resid ? pb.resid + (size_t)mw * g.ldr + n : nullptr;
+          float* cp = pb.C ? pb.C + off_c : nullptr;
+          __half* hp = pb.Ch ? pb.Ch + off_s : nullptr;
+          __half* lp = pb.Ch ? pb.Cl + off_s : nullptr;
+          const float* sp = scratch + lane;
+          if (rp) {
+            float rv[32];
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            if (r < rows) {
+            for (int r = 0; r < 32; ++r) rv[r] = r < rows ? rp[(size_t)r * g.ldr] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              if (r < rows) {
+                float v = (sp[r * 33] + bn) * scale;
+                if (relu) v = fmaxf(v, 0.f);
+                v += rv[r];
+                if (cp) cp[(size_t)r * str_c] = v;
+                if (hp) {
+                  __half hh, ll;
+                  if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
+                  else tc::split_h(v, hh, ll);
+                  hp[(size_t)r * str_s] = hh;
+                  lp[(size_t)r * str_s] = ll;
+                }
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
               float v = (sp[r * 33] + bn) * scale;
               if (relu) v = fmaxf(v, 0.f);
-              v += rv[r];
               if (cp) cp[(size_t)r * str_c] = v;
               if (hp) {
                 __half hh, ll;
@@ -180,28 +232,14 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
               }
             }
           }
-        } else {
-#pragma unroll 8
-          for (int r = 0; r < rows; ++r) {
-            float v = (sp[r * 33] + bn) * scale;
-            if (relu) v = fmaxf(v, 0.f);
-            if (cp) cp[(size_t)r * str_c] = v;
-            if (hp) {
-              __half hh, ll;
-              if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
-              else tc::split_h(v, hh, ll);
-              hp[(size_t)r * str_s] = hh;
-              lp[(size_t)r * str_s] = ll;
-            }
-          }
         }
+        __syncwarp();  // scratch is reused by the next column block / tile
       }
-      __syncwarp();  // scratch is reused by the next tile
     }
   }
   __syncwarp();
   if (!ok && g.err_flag) *g.err_flag = 1;
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, 4 * TM_N);
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }

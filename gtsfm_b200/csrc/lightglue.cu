@@ -32,6 +32,10 @@ struct ConfW {
 };
 }  // namespace
 
+constexpr int LG_MAX_PAIRS = 8;               // pairs walked in lock-step by one batch (b2_lightglue_match_batched_*)
+constexpr int LG_MAX_SIDES = 2 * LG_MAX_PAIRS;  // = GW_MAXP = AP_MAXP problems per launch
+static_assert(LG_MAX_SIDES <= GW_MAXP && LG_MAX_SIDES <= AP_MAXP, "batch does not fit one launch");
+
 struct LgSide {  // per-image workspace
   DevBuf x[2], xs[2], qkv, q, k, v, ctx, msg, h, hs, cs[2], sn[2], ind[2], conf, mat, src, md, rmax, rlog, ls, lsg, amax, aidx;
   int cur = 0;  // which of x / xs / cs / sn / ind is live
@@ -39,20 +43,34 @@ struct LgSide {  // per-image workspace
   int cap = 0;  // rows allocated; split-plane buffers keep their lo plane at +cap * width halves whatever n shrinks to
 };
 
+struct LgPair {  // one pair of the running batch: sides 2 * slot, 2 * slot + 1
+  bool active = false;  // still walking the layers
+  int n0 = 0, n1 = 0;   // keypoints handed in
+  int stop = 0;         // 0-based layer whose assignment head is used (lightglue.py:590-592)
+  long long* out_matches = nullptr;
+  float* out_scores = nullptr;
+};
+
 struct LightGlueState {
   bool loaded = false;
   int persist_ctas = 148;  // CTAs of the persistent kernels = SMs of the device minus the context's reserve_sms
   DevBuf wblob, wblob_h, wblob_l, errflag;  // fp32 weights + their split-fp16 (hi, lo * 2^11) copies for tcgen05
-  bool use_tc = true;                          // B2_FORCE_SIMT=1 keeps every GEMM on the exact-fp32 SIMT kernel
+  bool use_tc = true;                          // force_simt keeps every GEMM on the exact-fp32 SIMT kernel
   float* wr = nullptr;
   SelfW sw[LG_LAYERS];
   CrossW cw[LG_LAYERS];
   AssignW aw[LG_LAYERS];
   ConfW tw[LG_LAYERS - 1];
   float thr[LG_LAYERS];
-  LgSide side[2];
-  DevBuf sim, counters, bbox, outm, outs, attn_part[2], attn_ml[2];
+  LgSide side[LG_MAX_SIDES];
+  LgPair pair[LG_MAX_PAIRS];
+  DevBuf sim[LG_MAX_PAIRS], counters, attn_part, attn_ml, attn_cnt;
   HostBuf hread;
+};
+
+template <typename J>
+struct JobList {  // per-problem arguments of one batched launch; blockIdx.y (or .z) selects, n == 0 entries exit at once
+  J j[LG_MAX_SIDES];
 };
 
 void lg_destroy(b2_context* ctx) {
@@ -68,12 +86,9 @@ void lg_destroy(b2_context* ctx) {
                       &sd.rlog, &sd.ls, &sd.lsg, &sd.amax, &sd.aidx};
     for (DevBuf* b : bufs) b->release();
   }
-  s->sim.release();
-  for (int i = 0; i < 2; ++i) s->attn_part[i].release(), s->attn_ml[i].release();
+  for (auto& b : s->sim) b.release();
+  s->attn_part.release(), s->attn_ml.release(), s->attn_cnt.release();
   s->counters.release();
-  s->bbox.release();
-  s->outm.release();
-  s->outs.release();
   s->hread.release();
   delete s;
   ctx->lg = nullptr;
@@ -86,8 +101,20 @@ void lg_destroy(b2_context* ctx) {
 // normalize_keypoints with size=None (lightglue.py:31-43) + LearnableFourierPositionalEncoding (:68-81).  Every block
 // re-derives the bounding box (40 KB of keypoints, L2-resident) and then takes a grid-stride share of the n x 32
 // (cos, sin) table.  Also initialises ind[n] = n.
-__global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp, int n, const float* __restrict__ wr /*[32][2]*/,
-                                                     float* __restrict__ cs, float* __restrict__ sn, int* __restrict__ ind) {
+struct PosJob {
+  const float* kp;
+  int n;
+  float *cs, *sn;
+  int* ind;
+};
+__global__ void __launch_bounds__(1024) k_lg_posenc(const __grid_constant__ JobList<PosJob> jobs, const float* __restrict__ wr /*[32][2]*/) {
+  const PosJob& jb = jobs.j[blockIdx.y];
+  const float* __restrict__ kp = jb.kp;
+  const int n = jb.n;
+  float* __restrict__ cs = jb.cs;
+  float* __restrict__ sn = jb.sn;
+  int* __restrict__ ind = jb.ind;
+  if (n <= 0 || blockIdx.x * 1024 >= n * 32) return;  // (uniform per block)
   __shared__ float red[4][32];
   __shared__ float bb[4];
   float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
@@ -118,6 +145,28 @@ __global__ void __launch_bounds__(1024) k_lg_posenc(const float* __restrict__ kp
   for (int i = gtid; i < n; i += gsz) ind[i] = i;
 }
 
+// network input: x = desc (fp32 copy that the residual updates in place) + its split planes
+struct LoadJob {
+  const float* desc;
+  int n;
+  float* x;
+  __half *hi, *lo;  // null on the SIMT path
+};
+__global__ void __launch_bounds__(256) k_lg_load_desc(const __grid_constant__ JobList<LoadJob> jobs) {
+  const LoadJob& jb = jobs.j[blockIdx.y];
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= (size_t)jb.n * 256) return;
+  const float4 v = *reinterpret_cast<const float4*>(jb.desc + i);
+  *reinterpret_cast<float4*>(jb.x + i) = v;
+  if (jb.hi) {
+    uint32_t h01, l01, h23, l23;
+    tc::split2(v.x, v.y, h01, l01);
+    tc::split2(v.z, v.w, h23, l23);
+    *reinterpret_cast<uint2*>(jb.hi + i) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(jb.lo + i) = make_uint2(l01, l23);
+  }
+}
+
 // qkv [N][768] with feature (h*64 + j)*3 + {q,k,v} (lightglue.py:166-167) -> rotary on q,k (:58-65) -> [4][N][64],
 // either as fp32 (SIMT attention) or split into fp16 hi / lo planes (tcgen05 attention; plane stride = 4*N*64 halves).
 struct RotJob {  // one image's share of a two-image launch (blockIdx.y)
@@ -127,8 +176,8 @@ struct RotJob {  // one image's share of a two-image launch (blockIdx.y)
   void *qo, *ko, *vo;
 };
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) k_lg_split_rotary(RotJob j0, RotJob j1, int qk_unscaled) {
-  const RotJob& jb = blockIdx.y ? j1 : j0;
+__global__ void __launch_bounds__(256) k_lg_split_rotary(const __grid_constant__ JobList<RotJob> jobs, int qk_unscaled) {
+  const RotJob& jb = jobs.j[blockIdx.y];
   const float* __restrict__ qkv = jb.qkv;
   const float* __restrict__ cs = jb.cs;
   const float* __restrict__ sn = jb.sn;
@@ -176,8 +225,8 @@ struct LnJob {  // one image's share of a two-image launch (blockIdx.y)
   int n;
   __half *hi, *lo;
 };
-__global__ void __launch_bounds__(256) k_lg_ln_gelu(LnJob j0, LnJob j1, const float* __restrict__ g, const float* __restrict__ b) {
-  const LnJob& jb = blockIdx.y ? j1 : j0;
+__global__ void __launch_bounds__(256) k_lg_ln_gelu(const __grid_constant__ JobList<LnJob> jobs, const float* __restrict__ g, const float* __restrict__ b) {
+  const LnJob& jb = jobs.j[blockIdx.y];
   float* __restrict__ h = jb.h;
   __half* __restrict__ hi = jb.hi;
   __half* __restrict__ lo = jb.lo;
@@ -228,9 +277,9 @@ struct HeadJob {  // one image's share of a two-image launch (blockIdx.y)
   const float *w2, *b2;  // head 2 may be off for one image only (pruning threshold on the keypoint count)
   float *o1, *o2, *zraw;
 };
-__global__ void __launch_bounds__(256) k_lg_rowheads(HeadJob j0, HeadJob j1, const float* __restrict__ w1,
+__global__ void __launch_bounds__(256) k_lg_rowheads(const __grid_constant__ JobList<HeadJob> jobs, const float* __restrict__ w1,
                                                       const float* __restrict__ b1) {
-  const HeadJob& jb = blockIdx.y ? j1 : j0;
+  const HeadJob& jb = jobs.j[blockIdx.y];
   const float* __restrict__ x = jb.x;
   const float* __restrict__ w2 = jb.w2;
   const float* __restrict__ b2 = jb.b2;
@@ -266,14 +315,18 @@ __global__ void __launch_bounds__(256) k_lg_rowheads(HeadJob j0, HeadJob j1, con
 // pruning decision + ordered compaction map for one image (single block):
 //   counters[0 + side] += #(conf < thr)            (check_if_stop numerator, lightglue.py:653-655)
 //   keep = matchability > (1 - width_conf) | conf <= thr   (:636-643); src[pos] = old index; counters[2 + side] = #kept
-struct PruneJob {  // one image's share of a two-image launch (blockIdx.y = side)
+struct PruneJob {  // one image's share of a batched launch (blockIdx.y)
   const float *conf, *mat;
   int n;
   int* src;
+  int* counters;  // this image's pair: [0 + side] unconfident, [2 + side] kept
+  int side;
 };
-__global__ void __launch_bounds__(1024) k_lg_prune_plan(PruneJob j0, PruneJob j1, float thr, float keep_thr, int* __restrict__ counters) {
-  const int side = blockIdx.y;
-  const PruneJob& jb = side ? j1 : j0;
+__global__ void __launch_bounds__(1024) k_lg_prune_plan(const __grid_constant__ JobList<PruneJob> jobs, float thr, float keep_thr) {
+  const PruneJob& jb = jobs.j[blockIdx.y];
+  const int side = jb.side;
+  int* __restrict__ counters = jb.counters;
+  if (jb.n <= 0) return;
   const float* __restrict__ conf = jb.conf;
   const float* __restrict__ mat = jb.mat;
   int* __restrict__ src = jb.src;
@@ -318,25 +371,33 @@ __global__ void __launch_bounds__(1024) k_lg_prune_plan(PruneJob j0, PruneJob j1
 }
 
 // gather rows by src map: x [n][256], cos/sin [n][32], ind [n]  (lightglue.py:556-566)
-__global__ void __launch_bounds__(256) k_lg_gather(const int* __restrict__ src, const int* __restrict__ cnt,
-                                                    const float* __restrict__ x, const float* __restrict__ cs,
-                                                    const float* __restrict__ sn, const int* __restrict__ ind,
-                                                    float* __restrict__ x2, float* __restrict__ cs2, float* __restrict__ sn2,
-                                                    int* __restrict__ ind2, const __half* __restrict__ ph, size_t pstride,
-                                                    __half* __restrict__ ph2, size_t pstride2) {
+struct GatherJob {
+  const int *src, *cnt;
+  int n;  // rows before pruning (launch bound); *cnt rows are written
+  const float *x, *cs, *sn;
+  const int* ind;
+  float *x2, *cs2, *sn2;
+  int* ind2;
+  const __half* ph;  // split planes of x travel with it (null on the SIMT path)
+  size_t pstride;
+  __half* ph2;
+  size_t pstride2;
+};
+__global__ void __launch_bounds__(256) k_lg_gather(const __grid_constant__ JobList<GatherJob> jobs) {
+  const GatherJob& jb = jobs.j[blockIdx.y];
   int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= *cnt) return;
-  int s = src[r];
-  const float4* a = reinterpret_cast<const float4*>(x + (size_t)s * 256);
-  float4* o = reinterpret_cast<float4*>(x2 + (size_t)r * 256);
+  if (jb.n <= 0 || r >= *jb.cnt) return;
+  int s = jb.src[r];
+  const float4* a = reinterpret_cast<const float4*>(jb.x + (size_t)s * 256);
+  float4* o = reinterpret_cast<float4*>(jb.x2 + (size_t)r * 256);
   o[lane] = a[lane];
   o[lane + 32] = a[lane + 32];
-  cs2[r * 32 + lane] = cs[s * 32 + lane];
-  sn2[r * 32 + lane] = sn[s * 32 + lane];
-  if (lane == 0) ind2[r] = ind[s];
-  if (ph) {  // split planes of x travel with it: 256 halves = 32 lanes x 16 bytes per plane
-    reinterpret_cast<uint4*>(ph2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(ph + (size_t)s * 256)[lane];
-    reinterpret_cast<uint4*>(ph2 + pstride2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(ph + pstride + (size_t)s * 256)[lane];
+  jb.cs2[r * 32 + lane] = jb.cs[s * 32 + lane];
+  jb.sn2[r * 32 + lane] = jb.sn[s * 32 + lane];
+  if (lane == 0) jb.ind2[r] = jb.ind[s];
+  if (jb.ph) {  // 256 halves = 32 lanes x 16 bytes per plane
+    reinterpret_cast<uint4*>(jb.ph2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(jb.ph + (size_t)s * 256)[lane];
+    reinterpret_cast<uint4*>(jb.ph2 + jb.pstride2 + (size_t)r * 256)[lane] = reinterpret_cast<const uint4*>(jb.ph + jb.pstride + (size_t)s * 256)[lane];
   }
 }
 
@@ -593,33 +654,21 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
             s->wblob_h.as<__half>(), s->wblob_l.as<__half>());
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaDeviceSynchronize());
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   s->use_tc = !b2_force_simt(ctx);
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-  B2_CUDA(ctx, s->hread.ensure(64));
-  B2_CUDA(ctx, s->counters.ensure(64));
+  B2_CUDA(ctx, s->hread.ensure(8 * LG_MAX_PAIRS * sizeof(int)));
+  B2_CUDA(ctx, s->counters.ensure(8 * LG_MAX_PAIRS * sizeof(int)));
+  B2_CUDA(ctx, cudaMemset(s->counters.p, 0, 8 * LG_MAX_PAIRS * sizeof(int)));
   s->loaded = true;
   return B2_OK;
 }
 
 static inline TcWeights lg_tw(LightGlueState* s) {
   TcWeights t{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
-  const char* e = getenv("B2_NO_TMA");
-  t.use_tma = !(e && e[0] == '1');
-  t.attn_part = s->attn_part, t.attn_ml = s->attn_ml, t.sm_count = s->persist_ctas;
+  t.attn_part = &s->attn_part, t.attn_ml = &s->attn_ml, t.attn_cnt = &s->attn_cnt, t.sm_count = s->persist_ctas;
   return t;
-}
-static int lg_linear(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LinArgs& a, const LinArgs* b = nullptr) {
-  return run_linear(ctx, st, lg_tw(s), a, b);
-}
-static int lg_flash2(b2_context* ctx, cudaStream_t st, LightGlueState* s, const FlashJob& a, const FlashJob& b, float scale) {
-  return run_flash2(ctx, st, lg_tw(s), a, b, scale);
 }
 
 static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
@@ -648,14 +697,32 @@ static int lg_side_alloc(b2_context* ctx, LgSide& sd, int n) {
   return B2_OK;
 }
 
+// The sides (images) of the pairs that are still walking the layers, in launch order.
+struct LgActive {
+  int side[LG_MAX_SIDES];
+  int n = 0;
+};
+static LgActive lg_active_sides(const LightGlueState* s, int np) {
+  LgActive a;
+  for (int p = 0; p < np; ++p)
+    if (s->pair[p].active) a.side[a.n++] = 2 * p, a.side[a.n++] = 2 * p + 1;
+  return a;
+}
+static int lg_max_n(const LightGlueState* s, const LgActive& act) {
+  int mx = 0;
+  for (int i = 0; i < act.n; ++i) mx = s->side[act.side[i]].n > mx ? s->side[act.side[i]].n : mx;
+  return mx;
+}
+
 // x + ffn(cat[x, msg])  (lightglue.py:152-157,172,228-229): Linear(512,512) -> LN -> GELU -> Linear(512,256) + x, preceded
-// by the attention output projection (out_proj / to_out); both images of the pair go through each GEMM together.
-static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, const float* wout, const float* bout,
+// by the attention output projection (out_proj / to_out); every image of the batch goes through each GEMM together.
+static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, const float* wout, const float* bout,
                           const float* w0, const float* b0, const float* lng, const float* lnb, const float* w3, const float* b3) {
   int rc;
-  LinArgs o[2], f0[2], f3[2];
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
+  const TcWeights tw = lg_tw(s);
+  LinArgs o[LG_MAX_SIDES], f0[LG_MAX_SIDES], f3[LG_MAX_SIDES];
+  for (int i = 0; i < act.n; ++i) {
+    LgSide& sd = s->side[act.side[i]];
     const size_t e = (size_t)sd.cap * 256;
     float* x = sd.x[sd.cur].as<float>();
     LinArgs& a = o[i];
@@ -670,221 +737,297 @@ static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, c
     c.resid = x, c.ldr = 256;  // in place: every element is read (as residual) and written by the same thread
     c.cf = x, c.ldc = 256, c.tc_want_f32 = true, c.cp = planes_of(sd.xs[sd.cur], e), c.ldch = 256, c.M = sd.n, c.N = 256;
   }
-  if ((rc = lg_linear(ctx, st, s, o[0], &o[1]))) return rc;
-  if ((rc = lg_linear(ctx, st, s, f0[0], &f0[1]))) return rc;
+  if ((rc = run_linear(ctx, st, tw, o, act.n))) return rc;
+  if ((rc = run_linear(ctx, st, tw, f0, act.n))) return rc;
   {
-    LnJob lj[2];
-    int mx = 0;
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
+    JobList<LnJob> lj{};
+    for (int i = 0; i < act.n; ++i) {
+      LgSide& sd = s->side[act.side[i]];
       const Pl hs = planes_of(sd.hs, (size_t)sd.cap * 512);
-      lj[i] = {sd.h.as<float>(), sd.n, s->use_tc ? hs.hi : (__half*)nullptr, s->use_tc ? hs.lo : (__half*)nullptr};
-      mx = sd.n > mx ? sd.n : mx;
+      lj.j[i] = {sd.h.as<float>(), sd.n, s->use_tc ? hs.hi : (__half*)nullptr, s->use_tc ? hs.lo : (__half*)nullptr};
     }
+    const int mx = lg_max_n(s, act);
     if (mx > 0) {
-      B2_LAUNCH(ctx, k_lg_ln_gelu, dim3(cdiv(mx, 8), 2), 256, 0, st, lj[0], lj[1], lng, lnb);
+      B2_LAUNCH(ctx, k_lg_ln_gelu, dim3(cdiv(mx, 8), act.n), 256, 0, st, lj, lng, lnb);
       B2_CHECK_LAUNCH(ctx);
     }
   }
-  return lg_linear(ctx, st, s, f3[0], &f3[1]);
+  return run_linear(ctx, st, tw, f3, act.n);
 }
 
-static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
+static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer) {
   const SelfW& w = s->sw[layer];
+  const TcWeights tw = lg_tw(s);
   int rc;
-  LinArgs q[2];
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
+  LinArgs q[LG_MAX_SIDES];
+  for (int i = 0; i < act.n; ++i) {
+    LgSide& sd = s->side[act.side[i]];
     LinArgs& a = q[i];
     a.a1f = sd.x[sd.cur].as<float>(), a.a1p = planes_of(sd.xs[sd.cur], (size_t)sd.cap * 256), a.lda1 = 256, a.K1 = 256;
     a.w = w.wqkv, a.ldb = 256, a.bias = w.bqkv, a.cf = sd.qkv.as<float>(), a.ldc = 768, a.tc_want_f32 = true, a.M = sd.n, a.N = 768;
   }
-  if ((rc = lg_linear(ctx, st, s, q[0], &q[1]))) return rc;
+  if ((rc = run_linear(ctx, st, tw, q, act.n))) return rc;
   {
-    RotJob rj[2];
-    int mx = 0;
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
-      rj[i] = {sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p};
-      mx = sd.n > mx ? sd.n : mx;
+    JobList<RotJob> rj{};
+    for (int i = 0; i < act.n; ++i) {
+      LgSide& sd = s->side[act.side[i]];
+      rj.j[i] = {sd.qkv.as<float>(), sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.n, (size_t)sd.cap * 256, sd.q.p, sd.k.p, sd.v.p};
     }
+    const int mx = lg_max_n(s, act);
     if (mx > 0) {
-      if (s->use_tc)
-        B2_LAUNCH(ctx, k_lg_split_rotary<true>, dim3(cdiv(mx * 128, 256), 2), 256, 0, st, rj[0], rj[1],
-                  (attn_qk_unscaled(lg_tw(s)) ? 1 : 0) | (attn_v_unscaled(lg_tw(s)) ? 2 : 0));
+      if (s->use_tc)  // q, k, v all feed the TMEM-operand attention: unscaled lo planes (bits 0 and 1)
+        B2_LAUNCH(ctx, k_lg_split_rotary<true>, dim3(cdiv(mx * 128, 256), act.n), 256, 0, st, rj, 3);
       else
-        B2_LAUNCH(ctx, k_lg_split_rotary<false>, dim3(cdiv(mx * 128, 256), 2), 256, 0, st, rj[0], rj[1], 0);
+        B2_LAUNCH(ctx, k_lg_split_rotary<false>, dim3(cdiv(mx * 128, 256), act.n), 256, 0, st, rj, 0);
       B2_CHECK_LAUNCH(ctx);
     }
   }
-  LgSide &a = s->side[0], &b = s->side[1];
-  FlashJob ja{&a.q, &a.k, &a.v, &a.ctx, a.n, a.n, a.cap, a.cap}, jb{&b.q, &b.k, &b.v, &b.ctx, b.n, b.n, b.cap, b.cap};
-  if ((rc = lg_flash2(ctx, st, s, ja, jb, 0.125f))) return rc;
-  return lg_out_and_ffn(ctx, st, s, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
+  FlashJob fj[LG_MAX_SIDES];
+  for (int i = 0; i < act.n; ++i) {
+    LgSide& a = s->side[act.side[i]];
+    fj[i] = {&a.q, &a.k, &a.v, &a.ctx, a.n, a.n, a.cap, a.cap};
+  }
+  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f))) return rc;
+  return lg_out_and_ffn(ctx, st, s, act, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
-static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, int layer) {
+static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer) {
   const CrossW& w = s->cw[layer];
+  const TcWeights tw = lg_tw(s);
   int rc;
   for (int which = 0; which < 2; ++which) {  // to_qk -> sd.q, to_v -> sd.v, both head-major [4][n][64]
-    LinArgs p[2];
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
+    LinArgs p[LG_MAX_SIDES];
+    for (int i = 0; i < act.n; ++i) {
+      LgSide& sd = s->side[act.side[i]];
       const size_t e = (size_t)sd.cap * 256;
       LinArgs& a = p[i];
       a.a1f = sd.x[sd.cur].as<float>(), a.a1p = planes_of(sd.xs[sd.cur], e), a.lda1 = 256, a.K1 = 256;
       a.w = which ? w.wv : w.wqk, a.ldb = 256, a.bias = which ? w.bv : w.bqk;
       DevBuf& dst = which ? sd.v : sd.q;
       a.cf = dst.as<float>(), a.cp = planes_of(dst, e), a.head_major = 1, a.M = sd.n, a.N = 256;
-      a.lo_unscaled = (which == 0 ? attn_qk_unscaled(lg_tw(s)) : attn_v_unscaled(lg_tw(s))) ? 1 : 0;  // attention operands
+      a.lo_unscaled = s->use_tc ? 1 : 0;  // attention operands
     }
-    if ((rc = lg_linear(ctx, st, s, p[0], &p[1]))) return rc;
+    if ((rc = run_linear(ctx, st, tw, p, act.n))) return rc;
   }
   // m0 = softmax(s * qk0 qk1^T) v1 ; m1 = softmax(s * qk1 qk0^T) v0 with s = 64^-0.5 (the reference scales each
-  // operand by 64^-0.25, lightglue.py:216-221); both directions in one launch
-  LgSide &a = s->side[0], &b = s->side[1];
-  FlashJob ja{&a.q, &b.q, &b.v, &a.ctx, a.n, b.n, a.cap, b.cap}, jb{&b.q, &a.q, &a.v, &b.ctx, b.n, a.n, b.cap, a.cap};
-  if ((rc = lg_flash2(ctx, st, s, ja, jb, 0.125f))) return rc;
-  return lg_out_and_ffn(ctx, st, s, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
+  // operand by 64^-0.25, lightglue.py:216-221); both directions of every pair in one launch
+  FlashJob fj[LG_MAX_SIDES];
+  for (int i = 0; i < act.n; ++i) {
+    LgSide &a = s->side[act.side[i]], &b = s->side[act.side[i] ^ 1];
+    fj[i] = {&a.q, &b.q, &b.v, &a.ctx, a.n, b.n, a.cap, b.cap};
+  }
+  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f))) return rc;
+  return lg_out_and_ffn(ctx, st, s, act, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
-static int lg_match_impl(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
-                         const float* desc1, int n1, const b2_lightglue_params* prm, long long* out_matches,
-                         float* out_scores, int* out_k, int* out_stop, cudaStream_t st) {
+// One batch of up to LG_MAX_PAIRS pairs walked in lock-step (lightglue.py:474-629 for each of them).
+static int lg_match_batch(b2_context* ctx, b2_lightglue_pair* pairs, int np, const b2_lightglue_params* prm, cudaStream_t st) {
   LightGlueState* s = ctx->lg;
-  if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "lightglue weights not set");
-  s->persist_ctas = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
-  *out_k = 0;
-  *out_stop = 1;
-  if (n0 <= 0 || n1 <= 0) return B2_OK;  // lightglue.py:568-588 (no keypoints -> empty matches)
   int rc;
-  const float* kps[2] = {kp0, kp1};
-  const float* descs[2] = {desc0, desc1};
-  const int ns[2] = {n0, n1};
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    if ((rc = lg_side_alloc(ctx, sd, ns[i]))) return rc;
-    B2_CUDA(ctx, cudaMemcpyAsync(sd.x[0].p, descs[i], (size_t)ns[i] * 256 * 4, cudaMemcpyDeviceToDevice, st));
-    if (s->use_tc) {
-      const Pl xp = planes_of(sd.xs[0], (size_t)sd.cap * 256);
-      B2_LAUNCH(ctx, k_split_f32, (unsigned)cdiv(ns[i] * 256, 256), 256, 0, st, descs[i], (size_t)ns[i] * 256, xp.hi, xp.lo);
-      B2_CHECK_LAUNCH(ctx);
+  for (int p = 0; p < np; ++p) {
+    b2_lightglue_pair& pr = pairs[p];
+    pr.out_k = 0, pr.out_stop_layer = 1;
+    LgPair& lp = s->pair[p];
+    lp.n0 = pr.n0, lp.n1 = pr.n1, lp.stop = 0, lp.out_matches = (long long*)pr.out_matches, lp.out_scores = pr.out_scores;
+    lp.active = pr.n0 > 0 && pr.n1 > 0;  // lightglue.py:568-588 (no keypoints -> empty matches)
+    if (!lp.active) {
+      s->side[2 * p].n = s->side[2 * p + 1].n = 0;
+      continue;
     }
-    B2_LAUNCH(ctx, k_lg_posenc, ns[i] * 32 <= 1024 ? 1 : (cdiv(ns[i] * 32, 1024) < 148 ? cdiv(ns[i] * 32, 1024) : 148), 1024, 0, st, kps[i], ns[i], s->wr, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>());
+    if ((rc = lg_side_alloc(ctx, s->side[2 * p], pr.n0))) return rc;
+    if ((rc = lg_side_alloc(ctx, s->side[2 * p + 1], pr.n1))) return rc;
+  }
+  LgActive act = lg_active_sides(s, np);
+  if (act.n == 0) return B2_OK;
+  {
+    JobList<LoadJob> lj{};
+    JobList<PosJob> pj{};
+    for (int i = 0; i < act.n; ++i) {
+      const int sdi = act.side[i];
+      LgSide& sd = s->side[sdi];
+      const b2_lightglue_pair& pr = pairs[sdi >> 1];
+      const float* desc = (sdi & 1) ? pr.desc1 : pr.desc0;
+      const float* kp = (sdi & 1) ? pr.kp1 : pr.kp0;
+      const Pl xp = planes_of(sd.xs[0], (size_t)sd.cap * 256);
+      lj.j[i] = {desc, sd.n, sd.x[0].as<float>(), s->use_tc ? xp.hi : (__half*)nullptr, s->use_tc ? xp.lo : (__half*)nullptr};
+      pj.j[i] = {kp, sd.n, sd.cs[0].as<float>(), sd.sn[0].as<float>(), sd.ind[0].as<int>()};
+    }
+    const int mx = lg_max_n(s, act);
+    B2_LAUNCH(ctx, k_lg_load_desc, dim3(cdiv(mx * 64, 256), act.n), 256, 0, st, lj);
+    B2_CHECK_LAUNCH(ctx);
+    const int pb = cdiv(mx * 32, 1024);
+    B2_LAUNCH(ctx, k_lg_posenc, dim3(pb < 16 ? pb : 16, act.n), 1024, 0, st, pj, s->wr);
     B2_CHECK_LAUNCH(ctx);
   }
   const bool do_stop = prm->depth_confidence > 0.0, do_prune = prm->width_confidence > 0.0;
   const float keep_thr = (float)(1.0 - prm->width_confidence);  // scores > float32(1 - width_confidence)
   int* counters = s->counters.as<int>();
   int* hread = s->hread.as<int>();
-  int layer = 0;
-  for (layer = 0; layer < LG_LAYERS; ++layer) {
-    LgSide &a = s->side[0], &b = s->side[1];
-    if (a.n == 0 || b.n == 0) break;
-    if ((rc = lg_self_layer(ctx, st, s, layer))) return rc;
-    if ((rc = lg_cross_block(ctx, st, s, layer))) return rc;
+  for (int layer = 0; layer < LG_LAYERS && act.n > 0; ++layer) {
+    if ((rc = lg_self_layer(ctx, st, s, act, layer))) return rc;
+    if ((rc = lg_cross_block(ctx, st, s, act, layer))) return rc;
+    for (int p = 0; p < np; ++p)
+      if (s->pair[p].active) s->pair[p].stop = layer;
     if (layer == LG_LAYERS - 1) break;
     if (!do_stop && !do_prune) continue;
-    bool prune_side[2];
-    HeadJob hj[2];
-    PruneJob pj[2];
-    int mxn = 0;
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
+    bool prune_side[LG_MAX_SIDES];
+    JobList<HeadJob> hj{};
+    JobList<PruneJob> pj{};
+    for (int i = 0; i < act.n; ++i) {
+      const int sdi = act.side[i];
+      LgSide& sd = s->side[sdi];
       prune_side[i] = do_prune && sd.n > prm->prune_min_kpts;
-      hj[i] = {sd.x[sd.cur].as<float>(), sd.n, prune_side[i] ? s->aw[layer].wm : nullptr, prune_side[i] ? s->aw[layer].bm : nullptr,
-               sd.conf.as<float>(), sd.mat.as<float>(), nullptr};
-      pj[i] = {sd.conf.as<float>(), sd.mat.as<float>(), sd.n, sd.src.as<int>()};
-      mxn = sd.n > mxn ? sd.n : mxn;
+      hj.j[i] = {sd.x[sd.cur].as<float>(), sd.n, prune_side[i] ? s->aw[layer].wm : nullptr, prune_side[i] ? s->aw[layer].bm : nullptr,
+                 sd.conf.as<float>(), sd.mat.as<float>(), nullptr};
+      pj.j[i] = {sd.conf.as<float>(), sd.mat.as<float>(), sd.n, sd.src.as<int>(), counters + 4 * (sdi >> 1), sdi & 1};
     }
-    B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(mxn, 8), 2), 256, 0, st, hj[0], hj[1], do_stop ? s->tw[layer].w : nullptr,
+    const int mxn = lg_max_n(s, act);
+    B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(mxn, 8), act.n), 256, 0, st, hj, do_stop ? s->tw[layer].w : nullptr,
               do_stop ? s->tw[layer].b : nullptr);
     B2_CHECK_LAUNCH(ctx);
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
+    for (int i = 0; i < act.n; ++i) {
+      LgSide& sd = s->side[act.side[i]];
       if (!do_stop) B2_CUDA(ctx, cudaMemsetAsync(sd.conf.p, 0, (size_t)sd.n * 4, st));  // confidences None -> never "<= thr"
       if (!prune_side[i]) B2_CUDA(ctx, cudaMemsetAsync(sd.mat.p, 0x7f, (size_t)sd.n * 4, st));  // huge positive: keep all
     }
-    B2_LAUNCH(ctx, k_lg_prune_plan, dim3(1, 2), 1024, 0, st, pj[0], pj[1], do_stop ? s->thr[layer] : -1.0f, keep_thr, counters);
+    B2_LAUNCH(ctx, k_lg_prune_plan, dim3(1, act.n), 1024, 0, st, pj, do_stop ? s->thr[layer] : -1.0f, keep_thr);
     B2_CHECK_LAUNCH(ctx);
-    B2_CUDA(ctx, cudaMemcpyAsync(hread, counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaMemcpyAsync(hread, counters, 4 * LG_MAX_PAIRS * sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(ctx, cudaStreamSynchronize(st));
-    if (do_stop) {
-      // check_if_stop (lightglue.py:645-656) in float32: 1 - (#unconfident / (m + n)) > depth_confidence
-      float ratio = 1.0f - (float)(hread[0] + hread[1]) / (float)(n0 + n1);
-      if (ratio > (float)prm->depth_confidence) break;
-    }
-    for (int i = 0; i < 2; ++i) {
-      LgSide& sd = s->side[i];
-      if (!prune_side[i] || hread[2 + i] == sd.n) continue;  // nothing pruned: the buffers stay as they are
-      const float* x = sd.x[sd.cur].as<float>();
-      {
-        int nxt = sd.cur ^ 1;
-        B2_LAUNCH(ctx, k_lg_gather, cdiv(sd.n, 8), 256, 0, st, sd.src.as<int>(), counters + 2 + i, x,
-                  sd.cs[sd.cur].as<float>(), sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(),
-                  sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(), sd.ind[nxt].as<int>(),
-                  s->use_tc ? sd.xs[sd.cur].as<__half>() : (const __half*)nullptr, (size_t)sd.cap * 256, sd.xs[nxt].as<__half>(),
-                  (size_t)sd.cap * 256);
-        B2_CHECK_LAUNCH(ctx);
+    JobList<GatherJob> gj{};
+    int ng = 0, gmax = 0;
+    for (int p = 0; p < np; ++p) {
+      LgPair& lp = s->pair[p];
+      if (!lp.active) continue;
+      const int* hc = hread + 4 * p;
+      if (do_stop) {
+        // check_if_stop (lightglue.py:645-656) in float32: 1 - (#unconfident / (m + n)) > depth_confidence
+        const float ratio = 1.0f - (float)(hc[0] + hc[1]) / (float)(lp.n0 + lp.n1);
+        if (ratio > (float)prm->depth_confidence) {
+          lp.active = false;
+          continue;
+        }
       }
-      sd.cur ^= 1;
-      sd.n = hread[2 + i];
+      for (int side = 0; side < 2; ++side) {
+        LgSide& sd = s->side[2 * p + side];
+        const bool pruned = do_prune && sd.n > prm->prune_min_kpts;
+        if (!pruned || hc[2 + side] == sd.n) continue;  // nothing pruned: the buffers stay as they are
+        const int nxt = sd.cur ^ 1;
+        gj.j[ng++] = {sd.src.as<int>(), counters + 4 * p + 2 + side, sd.n, sd.x[sd.cur].as<float>(), sd.cs[sd.cur].as<float>(),
+                      sd.sn[sd.cur].as<float>(), sd.ind[sd.cur].as<int>(), sd.x[nxt].as<float>(), sd.cs[nxt].as<float>(), sd.sn[nxt].as<float>(),
+                      sd.ind[nxt].as<int>(), s->use_tc ? sd.xs[sd.cur].as<__half>() : (const __half*)nullptr, (size_t)sd.cap * 256,
+                      sd.xs[nxt].as<__half>(), (size_t)sd.cap * 256};
+        gmax = sd.n > gmax ? sd.n : gmax;
+        sd.cur = nxt;
+        sd.n = hc[2 + side];
+      }
+      if (s->side[2 * p].n == 0 || s->side[2 * p + 1].n == 0) lp.active = false;  // everything pruned away: no matches
     }
+    if (ng > 0) {
+      B2_LAUNCH(ctx, k_lg_gather, dim3(cdiv(gmax, 8), ng), 256, 0, st, gj);
+      B2_CHECK_LAUNCH(ctx);
+    }
+    act = lg_active_sides(s, np);
   }
-  if (layer == LG_LAYERS) layer = LG_LAYERS - 1;
-  *out_stop = layer + 1;
-  LgSide &a = s->side[0], &b = s->side[1];
-  if (a.n == 0 || b.n == 0) return B2_OK;
-  // MatchAssignment (lightglue.py:280-296) at the stopping layer
-  const AssignW& aw = s->aw[layer];
-  for (int i = 0; i < 2; ++i) {
-    LgSide& sd = s->side[i];
-    const float* x = sd.x[sd.cur].as<float>();
-    LinArgs g;
-    g.a1f = x, g.a1p = planes_of(sd.xs[sd.cur], (size_t)sd.cap * 256), g.lda1 = 256, g.K1 = 256, g.w = aw.wf, g.ldb = 256;
-    g.bias = aw.bf, g.scale = 0.25f;  // / 256 ** 0.25
-    g.cf = sd.md.as<float>(), g.ldc = 256, g.cp = planes_of(sd.md, (size_t)sd.cap * 256), g.ldch = 256, g.M = sd.n, g.N = 256;
-    if ((rc = lg_linear(ctx, st, s, g))) return rc;  // (the two images may stop with different sizes: separate launches)
-    {
-      HeadJob hj1{x, sd.n, aw.wm, aw.bm, nullptr, nullptr, sd.ls.as<float>()};
-      B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(sd.n, 8), 1), 256, 0, st, hj1, hj1, (const float*)nullptr, (const float*)nullptr);
+  // ---- MatchAssignment (lightglue.py:280-296) of every pair at its stopping layer -------------------------------------
+  const TcWeights tw = lg_tw(s);
+  int live[LG_MAX_PAIRS], nlive = 0;
+  for (int p = 0; p < np; ++p) {
+    pairs[p].out_stop_layer = s->pair[p].stop + 1;
+    if (s->pair[p].n0 > 0 && s->pair[p].n1 > 0 && s->side[2 * p].n > 0 && s->side[2 * p + 1].n > 0) live[nlive++] = p;
+  }
+  if (nlive == 0) return B2_OK;
+  for (int layer = 0; layer < LG_LAYERS; ++layer) {  // final_proj + matchability logits, grouped by stopping layer
+    LinArgs g[LG_MAX_SIDES];
+    JobList<HeadJob> hj{};
+    int ns = 0, mx = 0;
+    for (int li = 0; li < nlive; ++li) {
+      if (s->pair[live[li]].stop != layer) continue;
+      for (int side = 0; side < 2; ++side) {
+        LgSide& sd = s->side[2 * live[li] + side];
+        const float* x = sd.x[sd.cur].as<float>();
+        LinArgs& a = g[ns];
+        a.a1f = x, a.a1p = planes_of(sd.xs[sd.cur], (size_t)sd.cap * 256), a.lda1 = 256, a.K1 = 256, a.w = s->aw[layer].wf, a.ldb = 256;
+        a.bias = s->aw[layer].bf, a.scale = 0.25f;  // / 256 ** 0.25
+        a.cf = sd.md.as<float>(), a.ldc = 256, a.cp = planes_of(sd.md, (size_t)sd.cap * 256), a.ldch = 256, a.M = sd.n, a.N = 256;
+        hj.j[ns] = {x, sd.n, s->aw[layer].wm, s->aw[layer].bm, nullptr, nullptr, sd.ls.as<float>()};
+        mx = sd.n > mx ? sd.n : mx;
+        ++ns;
+      }
     }
+    if (ns == 0) continue;
+    if ((rc = run_linear(ctx, st, tw, g, ns))) return rc;
+    B2_LAUNCH(ctx, k_lg_rowheads, dim3(cdiv(mx, 8), ns), 256, 0, st, hj, (const float*)nullptr, (const float*)nullptr);
     B2_CHECK_LAUNCH(ctx);
   }
-  B2_CUDA(ctx, s->sim.ensure((size_t)a.n * b.n * 4));
-  LinArgs gs;
-  gs.a1f = a.md.as<float>(), gs.a1p = planes_of(a.md, (size_t)a.cap * 256), gs.lda1 = 256, gs.K1 = 256;
-  gs.bf = b.md.as<float>(), gs.bp = planes_of(b.md, (size_t)b.cap * 256), gs.ldb = 256;
-  gs.cf = s->sim.as<float>(), gs.ldc = b.n, gs.tc_want_f32 = true, gs.M = a.n, gs.N = b.n;
-  if ((rc = lg_linear(ctx, st, s, gs))) return rc;
-  const float* sim = s->sim.as<float>();
-  B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(), a.ls.as<float>(),
-            a.lsg.as<float>());
-  B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>(), b.ls.as<float>(),
-            b.lsg.as<float>());
-  B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_row_argmax, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
-            b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
-  B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
-            b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), b.aidx.as<int>());
-  B2_CHECK_LAUNCH(ctx);
-  B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,
-            (float)prm->filter_threshold, a.ind[a.cur].as<int>(), b.ind[b.cur].as<int>(), out_matches, out_scores, counters + 4);
-  B2_CHECK_LAUNCH(ctx);
-  B2_CUDA(ctx, cudaMemcpyAsync(hread + 4, counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
-  B2_CUDA(ctx, cudaStreamSynchronize(st));
-  *out_k = hread[4];
-  if (s->use_tc) {
-    int err = 0;
-    B2_CUDA(ctx, cudaMemcpyAsync(&err, s->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(ctx, cudaStreamSynchronize(st));
-    if (err) return b2_fail(ctx, B2_ERR_STATE, "tcgen05 pipeline timed out on an mbarrier (kernel bug)");
+  {  // sim = m0 m1^T of every pair: one launch, per-problem B operands
+    LinArgs gs[LG_MAX_PAIRS];
+    for (int li = 0; li < nlive; ++li) {
+      const int p = live[li];
+      LgSide &a = s->side[2 * p], &b = s->side[2 * p + 1];
+      B2_CUDA(ctx, s->sim[p].ensure((size_t)a.n * b.n * 4));
+      LinArgs& g = gs[li];
+      g.a1f = a.md.as<float>(), g.a1p = planes_of(a.md, (size_t)a.cap * 256), g.lda1 = 256, g.K1 = 256;
+      g.bf = b.md.as<float>(), g.bp = planes_of(b.md, (size_t)b.cap * 256), g.ldb = 256;
+      g.cf = s->sim[p].as<float>(), g.ldc = b.n, g.tc_want_f32 = true, g.M = a.n, g.N = b.n;
+    }
+    if ((rc = run_linear(ctx, st, tw, gs, nlive))) return rc;
   }
-  ctx->debug["lg_desc0"] = {a.x[a.cur].as<float>(), (int64_t)a.n * 256};
-  ctx->debug["lg_desc1"] = {b.x[b.cur].as<float>(), (int64_t)b.n * 256};
+  for (int li = 0; li < nlive; ++li) {
+    const int p = live[li];
+    LgSide &a = s->side[2 * p], &b = s->side[2 * p + 1];
+    const float* sim = s->sim[p].as<float>();
+    B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(), a.ls.as<float>(),
+              a.lsg.as<float>());
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_lg_col_stats, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, b.rmax.as<float>(), b.rlog.as<float>(), b.ls.as<float>(),
+              b.lsg.as<float>());
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_lg_row_argmax, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+              b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), a.amax.as<float>(), a.aidx.as<int>());
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
+              b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), b.aidx.as<int>());
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,
+              (float)prm->filter_threshold, a.ind[a.cur].as<int>(), b.ind[b.cur].as<int>(), s->pair[p].out_matches, s->pair[p].out_scores,
+              counters + 4 * LG_MAX_PAIRS + p);
+    B2_CHECK_LAUNCH(ctx);
+  }
+  B2_CUDA(ctx, cudaMemcpyAsync(hread + 4 * LG_MAX_PAIRS, counters + 4 * LG_MAX_PAIRS, LG_MAX_PAIRS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(hread + 5 * LG_MAX_PAIRS, s->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  if (s->use_tc && hread[5 * LG_MAX_PAIRS]) return b2_fail(ctx, B2_ERR_STATE, "tcgen05 pipeline timed out on an mbarrier (kernel bug)");
+  for (int li = 0; li < nlive; ++li) pairs[live[li]].out_k = hread[4 * LG_MAX_PAIRS + live[li]];
+  ctx->debug["lg_desc0"] = {s->side[0].x[s->side[0].cur].as<float>(), (int64_t)s->side[0].n * 256};
+  ctx->debug["lg_desc1"] = {s->side[1].x[s->side[1].cur].as<float>(), (int64_t)s->side[1].n * 256};
   return B2_OK;
+}
+
+static int lg_match_pairs(b2_context* ctx, b2_lightglue_pair* pairs, int n_pairs, const b2_lightglue_params* prm, cudaStream_t st) {
+  LightGlueState* s = ctx->lg;
+  if (!s || !s->loaded) return b2_fail(ctx, B2_ERR_STATE, "lightglue weights not set");
+  s->persist_ctas = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
+  const int bmax = ctx->lg_batch > 0 && ctx->lg_batch < LG_MAX_PAIRS ? ctx->lg_batch : LG_MAX_PAIRS;
+  for (int p0 = 0; p0 < n_pairs; p0 += bmax) {
+    const int np = n_pairs - p0 < bmax ? n_pairs - p0 : bmax;
+    int rc = lg_match_batch(ctx, pairs + p0, np, prm, st);
+    if (rc) return rc;
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_lightglue_match_batched_dev(b2_context* ctx, b2_lightglue_pair* pairs, int n_pairs, const b2_lightglue_params* params,
+                                              void* stream) {
+  if (!ctx || !params || n_pairs < 0 || (n_pairs > 0 && !pairs)) return B2_ERR_ARG;
+  for (int p = 0; p < n_pairs; ++p) {
+    const b2_lightglue_pair& pr = pairs[p];
+    if (pr.n0 < 0 || pr.n1 < 0) return B2_ERR_ARG;
+    if (pr.n0 > 0 && pr.n1 > 0 && (!pr.kp0 || !pr.desc0 || !pr.kp1 || !pr.desc1 || !pr.out_matches)) return B2_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return lg_match_pairs(ctx, pairs, n_pairs, params, (cudaStream_t)stream);
 }
 
 extern "C" int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
@@ -892,10 +1035,12 @@ extern "C" int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const f
                                       float* out_scores, int* out_k, int* out_stop_layer, void* stream) {
   if (!ctx || !params || !out_k || !out_stop_layer || n0 < 0 || n1 < 0) return B2_ERR_ARG;
   if (n0 > 0 && n1 > 0 && (!kp0 || !desc0 || !kp1 || !desc1 || !out_matches)) return B2_ERR_ARG;
+  b2_lightglue_pair pr{kp0, desc0, n0, kp1, desc1, n1, out_matches, out_scores, 0, 1};
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  return lg_match_impl(ctx, kp0, desc0, n0, kp1, desc1, n1, params, (long long*)out_matches, out_scores, out_k,
-                       out_stop_layer, (cudaStream_t)stream);
+  int rc = lg_match_pairs(ctx, &pr, 1, params, (cudaStream_t)stream);
+  *out_k = pr.out_k, *out_stop_layer = pr.out_stop_layer;
+  return rc;
 }
 
 
@@ -985,8 +1130,9 @@ extern "C" int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const 
       dkp[i] = static_cast<const float*>(a), ddesc[i] = static_cast<const float*>(b);
     }
   }
-  int rc = lg_match_impl(ctx, dkp[0], ddesc[0], n0, dkp[1], ddesc[1], n1, params, ctx->stage_d[5].as<long long>(),
-                         ctx->stage_d[6].as<float>(), out_k, out_stop_layer, st);
+  b2_lightglue_pair pr{dkp[0], ddesc[0], n0, dkp[1], ddesc[1], n1, ctx->stage_d[5].as<int64_t>(), ctx->stage_d[6].as<float>(), 0, 1};
+  int rc = lg_match_pairs(ctx, &pr, 1, params, st);
+  *out_k = pr.out_k, *out_stop_layer = pr.out_stop_layer;
   if (rc) return rc;
   if (*out_k > 0) {
     B2_CUDA(ctx, cudaMemcpyAsync(out_matches, ctx->stage_d[5].p, (size_t)*out_k * 2 * 8, cudaMemcpyDeviceToHost, st));

@@ -37,13 +37,13 @@ struct SuperGlueState {
   float *wf = nullptr, *bf = nullptr;
   float bin_score = 0.f;
   SgSide side[2];
-  DevBuf sim, counters, attn_part[2], attn_ml[2];
+  DevBuf sim, counters, attn_part, attn_ml, attn_cnt;
 };
 
 void sg_destroy(b2_context* ctx) {
   if (!ctx->sg) return;
   SuperGlueState* s = ctx->sg;
-  DevBuf* top[] = {&s->wblob, &s->wblob_h, &s->wblob_l, &s->errflag, &s->sim, &s->counters, &s->attn_part[0], &s->attn_part[1], &s->attn_ml[0], &s->attn_ml[1]};
+  DevBuf* top[] = {&s->wblob, &s->wblob_h, &s->wblob_l, &s->errflag, &s->sim, &s->counters, &s->attn_part, &s->attn_ml, &s->attn_cnt};
   for (DevBuf* b : top) b->release();
   for (auto& sd : s->side) {
     DevBuf* bufs[] = {&sd.x, &sd.xs, &sd.q, &sd.k, &sd.v, &sd.ctx, &sd.msg, &sd.h, &sd.hs, &sd.md, &sd.u, &sd.vv, &sd.best, &sd.arg};
@@ -330,12 +330,7 @@ extern "C" int b2_superglue_set_weights(b2_context* ctx, const float* blob, size
     w.w0 = next(), w.b0 = next(), w.w3 = next(), w.b3 = next();
   }
   s->wf = next(), s->bf = next();
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GEMM_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_GEMM_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   s->use_tc = !b2_force_simt(ctx);
@@ -351,11 +346,8 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
   *out_k = 0;
   if (n0 <= 0 || n1 <= 0) return B2_OK;  // superglue.py:233-240
   TcWeights tw{s->wblob.as<float>(), s->wblob_h.as<__half>(), s->wblob_l.as<__half>(), s->errflag.as<int>(), s->use_tc};
-  {
-    const char* e = getenv("B2_NO_TMA");
-    tw.use_tma = !(e && e[0] == '1');
-    tw.attn_part = s->attn_part, tw.attn_ml = s->attn_ml, tw.sm_count = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
-  }
+  tw.attn_part = &s->attn_part, tw.attn_ml = &s->attn_ml, tw.attn_cnt = &s->attn_cnt;
+  tw.sm_count = ctx->sm_count - ctx->reserve_sms > 0 ? ctx->sm_count - ctx->reserve_sms : 1;
   int rc;
   const float* kps[2] = {kp0, kp1};
   const float* scs[2] = {sc0, sc1};
@@ -395,13 +387,13 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
         g.a1f = sd.x.as<float>(), g.a1p = PL(sd.xs, sd.n, 256), g.lda1 = 256, g.K1 = 256, g.w = wts[which], g.ldb = 256, g.bias = bs[which];
         DevBuf& dst = which == 0 ? sd.q : (which == 1 ? sd.k : sd.v);
         g.cf = dst.as<float>(), g.cp = PL(dst, sd.n, 256), g.head_major = 1, g.M = sd.n, g.N = 256;
-        g.lo_unscaled = (which < 2 ? attn_qk_unscaled(tw) : attn_v_unscaled(tw)) ? 1 : 0;  // attention operands
+        g.lo_unscaled = tw.use_tc ? 1 : 0;  // attention operands
       }
-      if ((rc = run_linear(ctx, st, tw, p[0], &p[1]))) return rc;
+      if ((rc = run_linear(ctx, st, tw, p, 2))) return rc;
     }
     SgSide &sa = cross ? b : a, &sb = cross ? a : b;  // sources of image 0 / image 1
-    FlashJob ja{&a.q, &sa.k, &sa.v, &a.ctx, a.n, sa.n, a.n, sa.n}, jb{&b.q, &sb.k, &sb.v, &b.ctx, b.n, sb.n, b.n, sb.n};
-    if ((rc = run_flash2(ctx, st, tw, ja, jb, 0.125f))) return rc;
+    const FlashJob fj[2] = {{&a.q, &sa.k, &sa.v, &a.ctx, a.n, sa.n, a.n, sa.n}, {&b.q, &sb.k, &sb.v, &b.ctx, b.n, sb.n, b.n, sb.n}};
+    if ((rc = run_flash(ctx, st, tw, fj, 2, 0.125f))) return rc;
     LinArgs mg[2], f0[2], f3[2];
     for (int i = 0; i < 2; ++i) {
       SgSide& sd = s->side[i];
@@ -418,9 +410,9 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
       c.resid = sd.x.as<float>(), c.ldr = 256, c.cf = sd.x.as<float>(), c.ldc = 256, c.tc_want_f32 = true;
       c.cp = PL(sd.xs, sd.n, 256), c.ldch = 256, c.M = sd.n, c.N = 256;
     }
-    if ((rc = run_linear(ctx, st, tw, mg[0], &mg[1]))) return rc;
-    if ((rc = run_linear(ctx, st, tw, f0[0], &f0[1]))) return rc;
-    if ((rc = run_linear(ctx, st, tw, f3[0], &f3[1]))) return rc;
+    if ((rc = run_linear(ctx, st, tw, mg, 2))) return rc;
+    if ((rc = run_linear(ctx, st, tw, f0, 2))) return rc;
+    if ((rc = run_linear(ctx, st, tw, f3, 2))) return rc;
   }
   // final projection + score matrix / sqrt(256) (superglue.py:251-258)
   {
@@ -431,7 +423,7 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
       g.a1f = sd.x.as<float>(), g.a1p = PL(sd.xs, sd.n, 256), g.lda1 = 256, g.K1 = 256, g.w = s->wf, g.ldb = 256, g.bias = s->bf;
       g.cf = sd.md.as<float>(), g.ldc = 256, g.cp = PL(sd.md, sd.n, 256), g.ldch = 256, g.M = sd.n, g.N = 256;
     }
-    if ((rc = run_linear(ctx, st, tw, p[0], &p[1]))) return rc;
+    if ((rc = run_linear(ctx, st, tw, p, 2))) return rc;
   }
   const int M = a.n, N = b.n;
   B2_CUDA(ctx, s->sim.ensure((size_t)M * N * 4));
@@ -439,7 +431,7 @@ static int sg_match_impl(b2_context* ctx, const float* kp0, const float* sc0, co
   gs.a1f = a.md.as<float>(), gs.a1p = PL(a.md, a.n, 256), gs.lda1 = 256, gs.K1 = 256;
   gs.bf = b.md.as<float>(), gs.bp = PL(b.md, b.n, 256), gs.ldb = 256, gs.scale = 1.0f / 16.0f;
   gs.cf = s->sim.as<float>(), gs.ldc = N, gs.tc_want_f32 = true, gs.M = M, gs.N = N;
-  if ((rc = run_linear(ctx, st, tw, gs))) return rc;
+  if ((rc = run_linear(ctx, st, tw, &gs, 1))) return rc;
   // log-space Sinkhorn (superglue.py:141-170); u lives in a.u [M+1], v in b.vv [N+1]
   const float* Z = s->sim.as<float>();
   const float norm = -logf((float)(M + N));

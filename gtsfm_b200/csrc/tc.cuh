@@ -198,7 +198,10 @@ __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
 // x ~= hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significand bits, lo kept in fp16's normal range.
 constexpr float LO_SCALE = 2048.0f;
 constexpr float LO_INV = 1.0f / 2048.0f;
+constexpr float H_MAX = 65504.0f;  // the hi plane is fp16: values beyond its range SATURATE (no inf - inf = NaN in the lo plane)
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -H_MAX), H_MAX); }
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+  x = clamp_h(x);
   hi = __float2half_rn(x);
   lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
 }
@@ -206,6 +209,7 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
 // the attention logits' operands (q, k are O(1): lo only turns subnormal below |x| < 0.25, where its absolute error
 // <= 3e-8 is far under the logits' own fp32 rounding).
 __device__ __forceinline__ void split_h_unscaled(float x, __half& hi, __half& lo) {
+  x = clamp_h(x);
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
@@ -225,6 +229,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 // two floats -> packed (hi, hi) and (lo, lo) half2 words
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = clamp_h(a), b = clamp_h(b);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);

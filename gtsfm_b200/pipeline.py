@@ -10,7 +10,7 @@ from __future__ import annotations
 import contextlib
 import os
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -111,6 +111,26 @@ class DeviceFrontEnd:
                                              self._stream())
         self.ctx.check(rc, "lightglue_match_dev")
         return out[: k.value], stop.value
+
+    def match_batch(self, pairs: Sequence[Tuple[DeviceFeatures, DeviceFeatures]], depth_confidence=0.95, width_confidence=0.99,
+                    filter_threshold=0.1) -> List[Tuple[torch.Tensor, int]]:
+        """LightGlue over a list of pairs through `b2_lightglue_match_batched_dev`: the library walks up to 8 pairs in
+        lock-step (one launch per layer step for all their images).  -> [(matches (k, 2) int64 device tensor, stop layer)]."""
+        n = len(pairs)
+        if n == 0:
+            return []
+        arr = (_lib.LightGluePair * n)()
+        outs = []
+        for i, (a, b) in enumerate(pairs):
+            out = torch.empty((max(1, min(len(a), len(b))), 2), dtype=torch.int64, device=self.device)
+            outs.append(out)
+            arr[i].kp0, arr[i].desc0, arr[i].n0 = a.kp.data_ptr(), a.desc.data_ptr(), len(a)
+            arr[i].kp1, arr[i].desc1, arr[i].n1 = b.kp.data_ptr(), b.desc.data_ptr(), len(b)
+            arr[i].out_matches, arr[i].out_scores = out.data_ptr(), None
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min)
+        rc = self.lib.b2_lightglue_match_batched_dev(self.ctx.handle, arr, n, _lib.C.byref(prm), self._stream())
+        self.ctx.check(rc, "lightglue_match_batched_dev")
+        return [(outs[i][: arr[i].out_k], int(arr[i].out_stop_layer)) for i in range(n)]
 
     def verify_async(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1, cal2, threshold_px: float = 4.0,
                      seed: int = DEFAULT_SEED):

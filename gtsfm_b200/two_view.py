@@ -22,6 +22,7 @@ from .pipeline import DeviceFeatures, DeviceFrontEnd
 from .verifier import DEFAULT_SEED
 
 MIN_MATCHES_E = 6  # opencv_verifier_base.py:77-79
+MATCH_BATCH = 8    # pairs per lock-step LightGlue batch (the library maximum)
 
 
 @dataclass
@@ -53,19 +54,21 @@ class B200TwoViewBatch:
         """`putative[(i1, i2)]`: (k, 2) int64 device tensor of match indices; matched here with LightGlue when absent."""
         out: Dict[Tuple[int, int], TwoViewResult] = {}
         pending = []  # (pair, matches, future) in flight on the verification stream
-        for i1, i2 in pairs:
-            a, b = features[i1], features[i2]
-            if putative is not None and (i1, i2) in putative:
-                m = putative[(i1, i2)]
-            else:
-                m, _ = self.fe.match(a, b)
-            k = int(m.shape[0])
-            if k < MIN_MATCHES_E:
-                out[(i1, i2)] = _failure(k)
-                continue
-            fut = self.fe.verify_async(a, b, m, intrinsics[i1], intrinsics[i2], self.threshold_px, self.seed)
-            pending.append(((i1, i2), m, fut))
-            if len(pending) > 1:  # keep one verification in flight under the next pair's matching
+        pairs = list(pairs)
+        for c0 in range(0, len(pairs), MATCH_BATCH):
+            chunk = pairs[c0:c0 + MATCH_BATCH]
+            todo = [pr for pr in chunk if putative is None or pr not in putative]
+            matched = dict(zip(todo, self.fe.match_batch([(features[i1], features[i2]) for i1, i2 in todo])))
+            for i1, i2 in chunk:
+                a, b = features[i1], features[i2]
+                m = putative[(i1, i2)] if (i1, i2) not in matched else matched[(i1, i2)][0]
+                k = int(m.shape[0])
+                if k < MIN_MATCHES_E:
+                    out[(i1, i2)] = _failure(k)
+                    continue
+                # this chunk's verifications run on their own stream / thread under the next chunk's matching
+                pending.append(((i1, i2), m, self.fe.verify_async(a, b, m, intrinsics[i1], intrinsics[i2], self.threshold_px, self.seed)))
+            while len(pending) > MATCH_BATCH:
                 self._collect(pending.pop(0), out)
         for p in pending:
             self._collect(p, out)

@@ -47,6 +47,7 @@ uint64_t b2_h2d_bytes(const b2_context* ctx);
 /* Tuning knobs.  "reserve_sms" = n: the persistent kernels (attention, GEMM) launch sm_count - n CTAs, leaving n SMs to
  * kernels of OTHER contexts / streams running concurrently (the batched front-end overlaps pair k's RANSAC with pair
  * k+1's matching; a one-CTA-per-SM kernel that finds an SM busy would otherwise wait for a whole CTA lifetime).
+ * "lightglue_batch" = 0..8: pairs per lock-step batch of b2_lightglue_match_batched_dev (0 = 8, the maximum).
  * "force_simt" = 0 | 1: models whose weights are set afterwards run the exact-fp32 SIMT kernels instead of the tcgen05
  * split-fp16 ones (the on-device cross-check of the tensor-core path; tests only).
  * "feature_cache" = 0 | 1: drop every cached device copy of host feature arrays and (0, default) copy on every call like the
@@ -127,6 +128,27 @@ int b2_lightglue_match_dev(b2_context* ctx, const float* kp0, const float* desc0
 int b2_lightglue_match_host(b2_context* ctx, const float* kp0, const float* desc0, int n0, const float* kp1,
                             const float* desc1, int n1, const b2_lightglue_params* params, int64_t* out_matches,
                             float* out_scores, int* out_k, int* out_stop_layer);
+
+/* Batched variant (SURVEY.md 8b "_batched variants taking arrays of pairs"; the seam is
+ * gtsfm/frontend/correspondence_generator/det_desc_correspondence_generator.py:65-85, one matcher task per pair).  Up to 8
+ * pairs at a time are walked in lock-step: every linear layer, attention call and pruning step is ONE launch over all
+ * images of the batch, the per-layer early-exit / pruning counters of all pairs come back in one 128-byte read, pairs
+ * that stop early drop out of the later launches.  Results are identical to n_pairs calls of b2_lightglue_match_dev.
+ * All pointers inside `pairs` are DEVICE pointers; out_k / out_stop_layer are written on the HOST struct. */
+typedef struct b2_lightglue_pair {
+  const float* kp0;   /* [n0][2] (x, y) pixels */
+  const float* desc0; /* [n0][256] */
+  int n0;
+  const float* kp1;
+  const float* desc1;
+  int n1;
+  int64_t* out_matches; /* [min(n0, n1)][2] rows (idx0, idx1) ascending in idx0 */
+  float* out_scores;    /* [min(n0, n1)] or NULL */
+  int out_k;            /* written: number of matches */
+  int out_stop_layer;   /* written: 1-based stopping layer */
+} b2_lightglue_pair;
+int b2_lightglue_match_batched_dev(b2_context* ctx, b2_lightglue_pair* pairs, int n_pairs, const b2_lightglue_params* params,
+                                   void* stream);
 
 /* ---- SuperGlue --------------------------------------------------------------------------------------------------- */
 /* `blob`: packed fp32 tensors in gtsfm_b200/weights.py::SUPERGLUE_ORDER with eval-mode BatchNorm already folded

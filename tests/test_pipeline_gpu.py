@@ -49,3 +49,33 @@ def test_correspondence_generator_contract():
     for (i1, i2), m in matches.items():
         assert m.dtype == np.int64 and m.shape[1] == 2 and len(m) > 20
         assert m[:, 0].max() < len(kps[i1]) and m[:, 1].max() < len(kps[i2])
+
+
+def test_batched_match_equals_per_pair_and_golden(b200_ctx, golden_dir):
+    """b2_lightglue_match_batched_dev: 11 ragged pairs (> one batch of 8; different sizes, early exit, pruning, empty
+    image) walked in lock-step give exactly the rows of the per-pair entry point and of the reference fixtures."""
+    from gtsfm_b200.pipeline import DeviceFeatures
+
+    def feats(kp, sc, d, shape=(480, 640)):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        return DeviceFeatures(t(kp), t(sc), t(d), shape)
+
+    for profile, cases in (("stop", [(8, 512, 512), (10, 2048, 1900), (21, 200, 180), (22, 300, 0), (23, 64, 700), (24, 1500, 1400),
+                                      (25, 900, 901), (26, 333, 444), (27, 128, 128), (28, 1000, 256), (29, 50, 40)]),
+                           ("prune", [(7, 700, 640), (9, 37, 5), (31, 800, 800)])):
+        fe = DeviceFrontEnd(syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, profile), ctx=b200_ctx)
+        pairs = []
+        for seed, n0, n1 in cases:
+            kp0, sc0, d0, kp1, sc1, d1, _ = syn.synthetic_features(seed, max(n0, 1), max(n1, 1))
+            pairs.append((feats(kp0[:n0], sc0[:n0], d0[:n0]), feats(kp1[:n1], sc1[:n1], d1[:n1])))
+        batched = fe.match_batch(pairs)
+        stops = set()
+        for (a, b), (mb, sb), (seed, n0, n1) in zip(pairs, batched, cases):
+            ms, ss = fe.match(a, b)
+            assert sb == ss and np.array_equal(mb.cpu().numpy(), ms.cpu().numpy()), (profile, seed, n0, n1)
+            stops.add(sb)
+            tag = golden_dir / f"lightglue_{profile}_{seed}.npz"
+            if tag.exists():
+                fx = np.load(tag)
+                assert sb == int(fx["stop"]) and np.array_equal(mb.cpu().numpy(), fx["matches"])
+        assert len(stops) >= 2 or profile == "prune", "the batch should mix stopping layers"
