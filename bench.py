@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """bench.py — image-pairs/sec of the pairwise deep front-end hot path (detect + match + verify).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path, default workload
+    python bench.py --workload {vga_lightglue,mp1_lightglue,seq_superglue,superpoint_only,small_stop}
+    python bench.py --impl reference --gpus N --steps K ...        # the reference algorithm on the host CPU cores
+    python bench.py --scaling strong --frames F                    # ONE fixed job through the L2 seam, pairs sharded p mod world
 
-Workload (config.workload): the steady state of BASELINE.json configs[3] with the deep_front_end.yaml matcher —
-a synthetic 640x480 frame sequence, `Sequential(max_frame_lookahead=20)` pairs, SuperPoint (max 5000 keypoints) ->
-LightGlue -> RANSAC-5pt essential matrix.  One STEP = 2 new frames arriving: 2 detections + 40 pair matches + 40
-verifications against the 20-frame window whose features are resident.  Pairs shard across GPUs with no data-path
-collective (one weight broadcast at start-up), per-GPU work is fixed => "weak" scaling.
+Workloads (config.workload):
+  vga_lightglue   (default; the driver's line) steady state of BASELINE.json configs[3] with the deep_front_end.yaml matcher: synthetic
+                  640x480 sequence, Sequential(max_frame_lookahead=20), SuperPoint (<= 5000 keypoints) -> LightGlue (9 layers) ->
+                  RANSAC-5pt.  One STEP = 2 new frames: 2 detections + 40 matches + 40 verifications.
+  mp1_lightglue   configs[2]: 1024x1024 frames, SuperPoint -> LightGlue over all earlier frames.  STEP = 1 detection + 16 pairs.
+  seq_superglue   configs[3] verbatim: SuperPoint + SuperGlue (20 Sinkhorn iterations) + RANSAC-5pt.  STEP = 1 new frame + 20 pairs.
+  superpoint_only configs[1]: SuperPoint detect + describe only, 640x480.  STEP = 32 frames; metric = images/s.
+  small_stop      launch-bound regime: 1024 keypoints, 'stop' weights (early exit at layer 4-5, pruning on).  STEP = 40 pairs.
+Pairs shard across GPUs with no data-path collective (one weight broadcast at start-up); per-GPU work is fixed => "weak" scaling.
+`--scaling strong` instead times one fixed job (F frames, lookahead 20) through B200CorrespondenceGenerator + B200TwoViewBatch,
+including image (re-)detection on every rank and the final gather, wall-clock on rank 0.
 
-`value` times the device-resident path (frames already in HBM, features/matches stay in HBM, only per-pair scalars
-come back); `e2e` times the same step through the GTSfM plugin classes with HOST numpy buffers, so every H2D / D2H copy
-the per-call API implies is inside the timed region.
+`value` times the device-resident path (frames already in HBM, features / matches stay in HBM, only per-pair scalars come back);
+`e2e` times the same step through the GTSfM plugin classes with HOST numpy buffers, so every H2D / D2H copy the per-call API
+implies is inside the timed region (feature cache OFF, the default; `e2e.with_feature_cache` is the opt-in number beside it).
 """
 from __future__ import annotations
 
@@ -31,25 +39,46 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-H, W = 480, 640
-MAX_KP = 5000
-LOOKAHEAD = 20
-NEW_FRAMES = 2
-PAIRS_PER_STEP = LOOKAHEAD * NEW_FRAMES
 THR_PX = 4.0
 MATCH_BATCH = 8  # pairs per lock-step LightGlue batch (the library maximum)
-DOMINANT_KERNEL = "k_flash"  # prefix: k_flash_ps / k_flash_ts / k_flash_ws / k_flash_tc (tcgen05) or k_flash_attn (forced SIMT)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_flash_ps launch at this workload, from the `ncu --set full` capture
-# summarised in profiles/r01_flash_ps.txt (30.80 MB read + 0.68 MB written; the algorithmic minimum - q, k, v, o planes
-# of both images once - is 4 x 2 x 5000 x 256 x 4 B = 41 MB, i.e. K / V re-reads are served by L2)
-DOMINANT_KERNEL_DRAM_BYTES_PER_LAUNCH = 30.80e6 + 0.68e6
-CONFIG = {
-    "workload": "SuperPoint+LightGlue+RANSAC-5pt, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] steady state, deep_front_end.yaml matcher)",
-    "frame": [H, W], "max_keypoints": MAX_KP, "lookahead": LOOKAHEAD, "new_frames_per_step": NEW_FRAMES,
-    "pairs_per_step": PAIRS_PER_STEP, "lightglue": "9 layers, full depth (synthetic 'bench' weights: no early exit, nothing pruned)",
-    "ransac": "5pt, 1000 hypotheses, thr 4 px, conf 0.999999", "weights": "seeded synthetic (no checkpoint offline)",
-    "l2": "256 MiB flush between timed steps", "parallelism": "pairs sharded per GPU, no data-path collective",
+
+WORKLOADS = {
+    "vga_lightglue": dict(
+        H=480, W=640, max_kp=5000, matcher="lightglue", profile="bench", lookahead=20, new_frames=2, verify=True, dominant="k_flash",
+        text="SuperPoint+LightGlue+RANSAC-5pt, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] steady state, deep_front_end.yaml matcher)",
+        matcher_text="LightGlue 9 layers, full depth (synthetic 'bench' weights: no early exit, nothing pruned)"),
+    "mp1_lightglue": dict(
+        H=1024, W=1024, max_kp=5000, matcher="lightglue", profile="bench", lookahead=16, new_frames=1, verify=True, dominant="k_flash",
+        text="SuperPoint+LightGlue+RANSAC-5pt, synthetic 1024x1024 frames, each new frame against 16 resident frames (BASELINE configs[2]: "
+             "the full exhaustive job amortises one detection over 99.5 pairs; 1 per 16 here is pessimistic)",
+        matcher_text="LightGlue 9 layers, full depth (synthetic 'bench' weights)"),
+    "seq_superglue": dict(
+        H=480, W=640, max_kp=5000, matcher="superglue", profile="sharp", lookahead=20, new_frames=1, verify=True, dominant="k_flash",
+        text="SuperPoint+SuperGlue+RANSAC-5pt two-view, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] verbatim)",
+        matcher_text="SuperGlue 18 layers, 20 Sinkhorn iterations, threshold 0.2 (synthetic 'sharp' weights)"),
+    "superpoint_only": dict(
+        H=480, W=640, max_kp=5000, matcher=None, profile=None, lookahead=0, new_frames=32, verify=False, dominant="k_conv_tma",
+        text="SuperPoint detect+describe only, synthetic 640x480 frames (BASELINE configs[1])", matcher_text="-"),
+    "small_stop": dict(
+        H=480, W=640, max_kp=1024, matcher="lightglue", profile="stop", lookahead=20, new_frames=2, verify=True, dominant="k_flash",
+        text="SuperPoint (1024 keypoints)+LightGlue+RANSAC-5pt, 640x480 sequence, lookahead 20: the launch-/sync-bound regime (early exit + pruning fire)",
+        matcher_text="LightGlue 'stop' weights: early exit around layer 4-5, pruning at every layer (reference CPU semantics)"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures
+# (profiles/): per workload, or None where no capture of that workload's launch shape exists
+DOMINANT_DRAM_BYTES = {"vga_lightglue": None}
+
+
+def config_of(name: str) -> dict:
+    w = WORKLOADS[name]
+    pairs = w["lookahead"] * w["new_frames"]
+    return {
+        "workload": f"{name}: {w['text']}", "frame": [w["H"], w["W"]], "max_keypoints": w["max_kp"], "lookahead": w["lookahead"],
+        "new_frames_per_step": w["new_frames"], "pairs_per_step": pairs, "matcher": w["matcher_text"],
+        "match_batch": MATCH_BATCH if w["matcher"] == "lightglue" else 1,
+        "ransac": "5pt, 1000 hypotheses, thr 4 px, conf 0.999999" if w["verify"] else "-", "weights": "seeded synthetic (no checkpoint offline)",
+        "l2": "256 MiB flush between timed steps", "parallelism": "pairs sharded per GPU, no data-path collective",
+    }
 
 
 def measured_peaks():
@@ -94,85 +123,138 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
+#
+# Layouts timed: (a) ONE process with torch intra-op threads = t; (b) GTSfM's own layout, a pool of worker
+# PROCESSES with t threads each (gtsfm/runner.py:153-155: num_workers x threads_per_worker), every worker matching pairs
+# independently.  The faster is reported; `cores` = workers x t actually busy.
 # ------------------------------------------------------------------------------------------------------------------
-_BEST_THREADS = None
+_W = {}  # per-worker state of the process pool
 
 
-def best_cpu_threads(frames) -> int:
-    """torch's CPU kernels stop scaling (and then regress badly) well below the core count of a 100+-core host, so the CPU arm
-    is timed with the fastest intra-op thread count among {8, 16, 32, 64, all} on one SuperPoint detection — the reference's
-    own layout is a handful of threads per worker (gtsfm/runner.py:153-155)."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
+def _worker_init(wname: str, threads: int):
+    import cv2
     import torch
 
+    torch.set_num_threads(threads)
+    cv2.setNumThreads(threads)
     from gtsfm_b200 import synthetic as syn
     from oracle import superpoint_ref
 
-    cores = os.cpu_count() or 1
-    sd = syn.superpoint_state_dict(0)
-    best, best_t = cores, float("inf")
-    for n in sorted({min(c, cores) for c in (8, 16, 32, 64, cores)}):
-        torch.set_num_threads(n)
-        superpoint_ref.detect_and_describe(frames[0], sd, MAX_KP)
-        t0 = time.perf_counter()
-        superpoint_ref.detect_and_describe(frames[0], sd, MAX_KP)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-    _BEST_THREADS = best
-    return best
+    w = WORKLOADS[wname]
+    frames, cal = syn.synthetic_sequence(4, w["H"], w["W"])
+    sp_sd = syn.superpoint_state_dict(0)
+    _W.update(w=w, frames=frames, cal=cal, sp_sd=sp_sd)
+    if w["matcher"] == "lightglue":
+        _W["m_sd"] = syn.lightglue_state_dict(2, w["profile"])
+    elif w["matcher"] == "superglue":
+        _W["m_sd"] = syn.superglue_state_dict(1, w["profile"])
+    if w["matcher"]:
+        _W["fa"] = superpoint_ref.detect_and_describe(frames[0], sp_sd, w["max_kp"])
+        _W["fb"] = superpoint_ref.detect_and_describe(frames[2], sp_sd, w["max_kp"])
 
 
-def cpu_sample(frames, cal, n_pairs: int, threads: int):
-    """Bounded sample of the SAME workload on the CPU: 2 detections (one reused), n_pairs match+verify."""
-    import torch
+def _worker_task(kind: str):
+    """one unit of CPU work; returns (kind, seconds)"""
+    from oracle import lightglue_ref, superglue_ref, superpoint_ref, verifier_ref
 
-    from gtsfm_b200 import synthetic as syn
-    from oracle import lightglue_ref, superpoint_ref, verifier_ref
-
-    torch.set_num_threads(threads)
-    sp_sd, lg_sd = syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "bench")
+    w = _W["w"]
     t0 = time.perf_counter()
-    fa = superpoint_ref.detect_and_describe(frames[0], sp_sd, MAX_KP)
-    t_det = time.perf_counter() - t0
-    t_match = t_ver = 0.0
-    for j in range(n_pairs):
-        fb = superpoint_ref.detect_and_describe(frames[1 + j], sp_sd, MAX_KP)
-        t0 = time.perf_counter()
-        m = lightglue_ref.lightglue_match(fa[0], fa[2], fb[0], fb[2], lg_sd)
-        t_match += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        verifier_ref.verify_cv2(fa[0].astype(np.float64), fb[0].astype(np.float64), m.astype(np.uint32), cal, cal, True, THR_PX)
-        t_ver += time.perf_counter() - t0
-    per_pair = t_det / LOOKAHEAD + (t_match + t_ver) / n_pairs  # one detection serves `lookahead` pairs
-    return 1.0 / per_pair, {"detect_s_per_frame": t_det, "match_s_per_pair": t_match / n_pairs, "verify_s_per_pair": t_ver / n_pairs}
+    if kind == "detect":
+        superpoint_ref.detect_and_describe(_W["frames"][1], _W["sp_sd"], w["max_kp"])
+    else:  # one pair: match + verify
+        fa, fb = _W["fa"], _W["fb"]
+        shape = (w["H"], w["W"], 3)
+        if w["matcher"] == "lightglue":
+            m = lightglue_ref.lightglue_match(fa[0], fa[2], fb[0], fb[2], _W["m_sd"])
+        else:
+            m = superglue_ref.superglue_match(fa[0], fa[1], fa[2], fb[0], fb[1], fb[2], shape, shape, _W["m_sd"])
+        if w["verify"]:
+            verifier_ref.verify_cv2(fa[0].astype(np.float64), fb[0].astype(np.float64), m.astype(np.uint32), _W["cal"], _W["cal"], True, THR_PX)
+    return kind, time.perf_counter() - t0
+
+
+def cpu_layout_rate(wname: str, workers: int, threads: int, units_per_worker: int = 1):
+    """Throughput of `workers` processes x `threads` threads on this workload -> (units per second of the metric, stage dict)."""
+    import multiprocessing as mp
+
+    w = WORKLOADS[wname]
+    kinds = ["detect"] if not w["matcher"] else ["pair", "detect"]
+    stages = {}
+    if workers == 1:
+        _worker_init(wname, threads)
+        run = lambda kind, n: [_worker_task(kind) for _ in range(n)]  # noqa: E731
+        pool = None
+    else:
+        pool = mp.get_context("spawn").Pool(workers, initializer=_worker_init, initargs=(wname, threads))
+        run = lambda kind, n: pool.map(_worker_task, [kind] * n, chunksize=1)  # noqa: E731
+    try:
+        for kind in kinds:
+            warm = run(kind, workers)  # warm-up (imports, first touch) outside the timed span; also sizes the sample: >= ~3 s per stage
+            t_unit = max(1e-3, float(np.mean([r[1] for r in warm])))
+            n = workers * max(units_per_worker, min(8, int(np.ceil(3.0 / t_unit))))
+            t0 = time.perf_counter()
+            res = run(kind, n)
+            wall = time.perf_counter() - t0
+            stages[f"{kind}_per_sec"] = n / wall
+            stages[f"{kind}_s_each"] = float(np.mean([r[1] for r in res]))
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+    if not w["matcher"]:
+        return stages["detect_per_sec"], stages
+    # one detection serves `lookahead` pairs; detection and matching share the same cores
+    per_pair = 1.0 / stages["pair_per_sec"] + (1.0 / stages["detect_per_sec"]) / max(1, w["lookahead"])
+    return 1.0 / per_pair, stages
+
+
+def cpu_baseline(wname: str, quick: bool):
+    """Best CPU layout for this workload.  quick (the default CUDA run's `cpu_baseline` leg): two layouts, ~20-30 s; otherwise
+    (`--impl reference`) the fuller sweep."""
+    cores = os.cpu_count() or 1
+    if quick:
+        layouts = [(1, min(32, cores)), (max(1, cores // 8), 8)] if cores >= 16 else [(1, cores)]
+    else:
+        layouts = [(1, min(32, cores)), (1, min(64, cores))]
+        layouts += [(max(1, cores // t), t) for t in (16, 8, 4) if cores // t >= 2]
+    best = None
+    tried = []
+    for workers, threads in layouts:
+        try:
+            v, stages = cpu_layout_rate(wname, workers, threads)
+        except Exception as e:  # a layout that cannot run (memory) must not sink the line
+            tried.append({"workers": workers, "threads": threads, "error": repr(e)[:120]})
+            continue
+        tried.append({"workers": workers, "threads": threads, "value": v})
+        if best is None or v > best[0]:
+            best = (v, workers, threads, stages)
+    v, workers, threads, stages = best
+    w = WORKLOADS[wname]
+    unit = "images/s" if not w["matcher"] else "pairs/s"
+    sample = (f"oracle port (torch-CPU fp32 + cv2 USAC) on the host cores; layout = {workers} process(es) x {threads} threads (best of "
+              f"{[(t['workers'], t['threads']) for t in tried]}); per layout: every worker runs 1 pair (match+verify at "
+              f"{w['max_kp']} keypoints) and 1 detection, timed wall-clock across the pool; "
+              + ("images/s = detections/s" if not w["matcher"] else f"pairs/s = 1 / (1/pair_rate + (1/detect_rate)/{max(1, w['lookahead'])})"))
+    return {"value": v, "unit": unit, "cores": workers * threads, "host_cores": cores, "kind": "port", "layout": {"processes": workers, "threads_each": threads},
+            "sample": sample, "stages": stages, "layouts_tried": tried}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from gtsfm_b200 import synthetic as syn
-
-    frames, cal = syn.synthetic_sequence(4)
-    cores = best_cpu_threads(frames)
-    vals, stages = [], {}
-    for i in range(args.warmup_ref + args.steps):
-        v, stages = cpu_sample(frames, cal, 1, cores)
-        if i >= args.warmup_ref:
-            vals.append(v)
+    w = WORKLOADS[args.workload]
+    vals, cb = [], None
+    for i in range(max(1, min(args.steps, 2))):  # each "step" is one bounded sweep of the layouts (tens of seconds)
+        cb = cpu_baseline(args.workload, quick=False)
+        vals.append(cb["value"])
     value = float(np.mean(vals))
-    sample = "per step: 1 SuperPoint detection + 1 LightGlue pair (5000x5000 keypoints, 9 layers) + 1 cv2 USAC verification; " \
-             "pairs/s = 1 / (t_detect/20 + t_match + t_verify)"
+    cb["value"] = value
     line = {
-        "impl": "reference", "metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup_ref, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": CONFIG,
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port", "sample": sample, "stages": stages},
-        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": "images_per_sec" if not w["matcher"] else "image_pairs_per_sec", "value": value, "unit": cb["unit"],
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args.workload), "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
     }
     print(json.dumps(line))
 
@@ -180,16 +262,9 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_cuda(args):
+def _setup_dist():
     import torch
     import torch.distributed as dist
-
-    from gtsfm_b200 import _lib, synthetic as syn, weights
-    from gtsfm_b200.detector_descriptor import B200SuperPointDetectorDescriptor
-    from gtsfm_b200.gtsfm_api import Cal3Bundler, Image
-    from gtsfm_b200.matcher import B200LightGlueMatcher
-    from gtsfm_b200.pipeline import DeviceFrontEnd
-    from gtsfm_b200.verifier import B200Ransac
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -198,40 +273,87 @@ def run_cuda(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # weights: rank 0 materialises them, one NCCL broadcast at start-up
-    sp_sd, lg_sd = syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "bench")
-    if world > 1:
-        for sd, order in ((sp_sd, weights.SUPERPOINT_ORDER), (lg_sd, weights.LIGHTGLUE_ORDER)):
-            blob = torch.from_numpy(np.concatenate([np.asarray(sd[k], np.float32).ravel() for k in order])).to(dev)
-            dist.broadcast(blob, 0)
-            flat, off = blob.cpu().numpy(), 0
-            for k in order:
-                n = int(np.prod(sd[k].shape)) if sd[k].shape else 1
-                sd[k] = flat[off:off + n].reshape(sd[k].shape)
-                off += n
-    fe = DeviceFrontEnd(sp_sd, lg_sd, device=local, max_keypoints=MAX_KP)
-    n_frames = LOOKAHEAD + NEW_FRAMES * (args.warmup + args.steps) * 2 + 4
+    return rank, world, local, dev
+
+
+def _broadcast_weights(sds, world, dev):
+    """rank 0 materialises the weights, one NCCL broadcast per model at start-up"""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return
+    for sd, order in sds:
+        blob = torch.from_numpy(np.concatenate([np.asarray(sd[k], np.float32).ravel() for k in order])).to(dev)
+        dist.broadcast(blob, 0)
+        flat, off = blob.cpu().numpy(), 0
+        for k in order:
+            n = int(np.prod(sd[k].shape)) if sd[k].shape else 1
+            sd[k] = flat[off:off + n].reshape(sd[k].shape)
+            off += n
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from gtsfm_b200 import synthetic as syn, weights
+    from gtsfm_b200.detector_descriptor import B200SuperPointDetectorDescriptor
+    from gtsfm_b200.gtsfm_api import Cal3Bundler, Image
+    from gtsfm_b200.matcher import B200LightGlueMatcher, B200SuperGlueMatcher
+    from gtsfm_b200.pipeline import DeviceFrontEnd
+    from gtsfm_b200.verifier import B200Ransac
+
+    wname = args.workload
+    w = WORKLOADS[wname]
+    H, W, MAX_KP, LOOKAHEAD, NEW_FRAMES = w["H"], w["W"], w["max_kp"], w["lookahead"], w["new_frames"]
+    units_per_step = NEW_FRAMES if not w["matcher"] else LOOKAHEAD * NEW_FRAMES
+    rank, world, local, dev = _setup_dist()
+    sp_sd = syn.superpoint_state_dict(0)
+    lg_sd = syn.lightglue_state_dict(2, w["profile"]) if w["matcher"] == "lightglue" else None
+    sg_sd = syn.superglue_state_dict(1, w["profile"]) if w["matcher"] == "superglue" else None
+    sds = [(sp_sd, weights.SUPERPOINT_ORDER)]
+    if lg_sd is not None:
+        sds.append((lg_sd, weights.LIGHTGLUE_ORDER))
+    _broadcast_weights(sds, world, dev)
+    fe = DeviceFrontEnd(sp_sd, lg_sd, device=local, max_keypoints=MAX_KP, superglue_sd=sg_sd)
+    if args.lg_batch:
+        fe.ctx.set_option("lightglue_batch", args.lg_batch)
+    n_frames = max(LOOKAHEAD, 1) + NEW_FRAMES * (args.warmup + args.steps) * 2 + 4
+    n_frames = min(n_frames, 96) if not w["matcher"] else n_frames  # detect-only: frames are re-used round robin
     # each rank works on its own stretch of the sequence (weak scaling): different seed per rank
     frames, cal = syn.synthetic_sequence(n_frames, H, W, seed=77 + rank)
     frames_dev = [torch.from_numpy(f).to(dev) for f in frames]
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    window = deque(maxlen=LOOKAHEAD)
+    window = deque(maxlen=max(LOOKAHEAD, 1))
     for i in range(LOOKAHEAD):
         window.append(fe.detect(frames_dev[i]))
     cursor = LOOKAHEAD
-    stats = {"matches": 0, "inliers": 0, "pairs": 0}
+    stats = {"matches": 0, "inliers": 0, "pairs": 0, "stops": 0, "keypoints": 0, "frames": 0}
 
     def step_device(c):
         pending = []
         for j in range(NEW_FRAMES):
-            f = fe.detect(frames_dev[c + j])
+            f = fe.detect(frames_dev[(c + j) % len(frames_dev)])
+            stats["keypoints"] += len(f)
+            stats["frames"] += 1
+            if not w["matcher"]:
+                continue
             prevs = list(window)
-            for b0 in range(0, len(prevs), MATCH_BATCH):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
-                chunk = prevs[b0:b0 + MATCH_BATCH]
-                for prev, (m, _) in zip(chunk, fe.match_batch([(prev, f) for prev in chunk])):
-                    pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next batch's matcher kernels
+            if w["matcher"] == "lightglue":
+                for b0 in range(0, len(prevs), MATCH_BATCH):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
+                    chunk = prevs[b0:b0 + MATCH_BATCH]
+                    for prev, (m, stop) in zip(chunk, fe.match_batch([(prev, f) for prev in chunk])):
+                        pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next batch's matcher kernels
+                        stats["matches"] += int(m.shape[0])
+                        stats["stops"] += stop
+                        stats["pairs"] += 1
+            else:
+                for prev in prevs:
+                    m = fe.match_superglue(prev, f)
+                    pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))
                     stats["matches"] += int(m.shape[0])
                     stats["pairs"] += 1
             window.append(f)
@@ -241,7 +363,8 @@ def run_cuda(args):
     for _ in range(args.warmup):
         step_device(cursor)
         cursor += NEW_FRAMES
-    stats.update(matches=0, inliers=0, pairs=0)
+    for k in stats:
+        stats[k] = 0
 
     def barrier():
         if world > 1:
@@ -253,7 +376,7 @@ def run_cuda(args):
     sampler.start()
     launches0 = fe.ctx.launch_count()
     vlaunch0 = fe._vctx.launch_count() if fe._vctx else 0
-    fe.ctx.profile_start(DOMINANT_KERNEL)
+    fe.ctx.profile_start(w["dominant"])
     total_ms = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.steps):
@@ -265,9 +388,26 @@ def run_cuda(args):
         torch.cuda.synchronize()
         total_ms += e0.elapsed_time(e1)
         cursor += NEW_FRAMES
-    k_ms, k_launches, k_flop = fe.ctx.profile_stop()
+    k_ms, k_launches, k_work = fe.ctx.profile_stop()
     launches = fe.ctx.launch_count() - launches0 + (fe._vctx.launch_count() - vlaunch0 if fe._vctx else 0)
-    # secondary figures (untimed region): detect-only rate (BASELINE configs[1] shape) and the encoder convolutions' rate
+    # secondary figures (untimed region): where the rest of the step goes - one extra step per kernel family, CUDA events around
+    # every launch of that family on its launching stream (the verification kernels run on their own context / stream)
+    family_ms = {}
+    if w["matcher"]:
+        for fam in ("k_gemm_ws", "k_lg_", "k_sg_", "k_conv", "k_nms", "k_head"):
+            fe.ctx.profile_start(fam)
+            step_device(cursor)
+            torch.cuda.synchronize()
+            ms, n, _ = fe.ctx.profile_stop()
+            if n:
+                family_ms[fam] = {"ms_per_step": ms, "launches": n}
+        if fe._vctx is not None:
+            fe._vctx.profile_start("k_rs_")
+            step_device(cursor)
+            torch.cuda.synchronize()
+            ms, n, _ = fe._vctx.profile_stop()
+            family_ms["k_rs_ (verification stream, overlapped)"] = {"ms_per_step": ms, "launches": n}
+    # detect-only rate (BASELINE configs[1] shape) and the encoder convolutions' rate
     torch.cuda.synchronize()
     fe.ctx.profile_start("k_conv_tma")
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,78 +424,163 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
-    pairs_total = PAIRS_PER_STEP * args.steps * world
-    value = pairs_total / (max_ms / 1000.0)
+    units_total = units_per_step * args.steps * world
+    value = units_total / (max_ms / 1000.0)
 
     # ---- e2e: the same step through the GTSfM plugin API with host buffers ------------------------------------------
     det = B200SuperPointDetectorDescriptor(max_keypoints=MAX_KP, weights_path=sp_sd, device=local)
-    mat = B200LightGlueMatcher("superpoint", weights_path=lg_sd, device=local)
-    ver = B200Ransac(True, THR_PX, device=local)
     calib = Cal3Bundler(cal[0], 0, 0, cal[1], cal[2])
-    hwin = deque(maxlen=LOOKAHEAD)
-    for i in range(LOOKAHEAD):
-        hwin.append(det.detect_and_describe(Image(frames[i])))
-    def step_host(c):
-        for j in range(NEW_FRAMES):
-            kps, desc = det.detect_and_describe(Image(frames[c + j]))
-            for pk, pd in list(hwin):
-                m = mat.match(pk, kps, pd, desc, (H, W, 3), (H, W, 3))
-                ver.verify(pk, kps, m, calib, calib)
-            hwin.append((kps, desc))
 
-    def copied():
-        engs = [det._engine, mat._engine, ver._engine]
-        return sum(e.h2d_bytes for e in engs if e), sum(e.d2h_bytes for e in engs if e)
+    def make_matcher(cache: bool):
+        if w["matcher"] == "lightglue":
+            return B200LightGlueMatcher("superpoint", weights_path=lg_sd, device=local, feature_cache=cache)
+        if w["matcher"] == "superglue":
+            return B200SuperGlueMatcher(weights_path=sg_sd, device=local)
+        return None
 
-    c2 = LOOKAHEAD
-    for _ in range(min(args.warmup, 3)):
-        step_host(c2)
-        c2 += NEW_FRAMES
-    barrier()
-    h2d0, d2h0 = copied()
-    e2e_wall = 0.0
-    for i in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step_host(c2)
-        torch.cuda.synchronize()
-        e2e_wall += time.perf_counter() - t0
-        c2 += NEW_FRAMES
-    barrier()
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_total / float(t.item())
-    h2d1, d2h1 = copied()
-    traffic = {"h2d": (h2d1 - h2d0) // args.steps, "d2h": (d2h1 - d2h0) // args.steps}
+    def e2e_run(cache: bool, steps: int):
+        mat = make_matcher(cache)
+        ver = B200Ransac(True, THR_PX, device=local) if w["verify"] else None
+        hwin = deque(maxlen=max(LOOKAHEAD, 1))
+        for i in range(LOOKAHEAD):
+            hwin.append(det.detect_and_describe(Image(frames[i])))
+
+        def step_host(c):
+            for j in range(NEW_FRAMES):
+                kps, desc = det.detect_and_describe(Image(frames[(c + j) % len(frames)]))
+                if mat is None:
+                    continue
+                for pk, pd in list(hwin):
+                    m = mat.match(pk, kps, pd, desc, (H, W, 3), (H, W, 3))
+                    if ver is not None:
+                        ver.verify(pk, kps, m, calib, calib)
+                hwin.append((kps, desc))
+
+        def copied():
+            engs = [det._engine, mat._engine if mat else None, ver._engine if ver else None]
+            return sum(e.h2d_bytes for e in engs if e), sum(e.d2h_bytes for e in engs if e)
+
+        c2 = LOOKAHEAD
+        for _ in range(min(args.warmup, 2)):
+            step_host(c2)
+            c2 += NEW_FRAMES
+        barrier()
+        h2d0, d2h0 = copied()
+        wall = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_host(c2)
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            c2 += NEW_FRAMES
+        barrier()
+        tt = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d1, d2h1 = copied()
+        return units_per_step * steps * world / float(tt.item()), (h2d1 - h2d0) // steps, (d2h1 - d2h0) // steps
+
+    if args.no_e2e:
+        e2e_value, h2d, d2h = float("nan"), 0, 0
+    else:
+        e2e_value, h2d, d2h = e2e_run(False, args.steps)
+    e2e = {"value": e2e_value, "unit": "images/s" if not w["matcher"] else "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "feature_cache": "off (default: every call uploads its arrays, like the reference)"}
+    if w["matcher"] == "lightglue" and not args.no_e2e:
+        v2, h2, _ = e2e_run(True, max(1, args.steps - 1))
+        e2e["with_feature_cache"] = {"value": v2, "h2d_bytes_per_step": int(h2), "note": "opt-in B200LightGlueMatcher(feature_cache=True), full-content hash"}
 
     if rank == 0:
         tf_peak, hbm_peak, peak_src = measured_peaks()
-        achieved = (k_flop / 1e12) / (k_ms / 1e3) if k_ms > 0 else 0.0
+        achieved = (k_work / 1e12) / (k_ms / 1e3) if k_ms > 0 else 0.0
+        unit = "images/s" if not w["matcher"] else "pairs/s"
         line = {
-            "metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": CONFIG, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": traffic["h2d"], "d2h_bytes_per_step": traffic["d2h"]},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": DOMINANT_KERNEL, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": DOMINANT_KERNEL_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r01_flash_ps.txt)", "peak_source": f"bf16_tflops_sustained ({peak_src})",
+            "metric": "images_per_sec" if not w["matcher"] else "image_pairs_per_sec", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_of(wname), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": w["dominant"], "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf_peak, "traffic": DOMINANT_DRAM_BYTES.get(wname),
+                         "traffic_unit": "dram bytes per launch (ncu --set full capture under profiles/), null = not captured for this launch shape",
+                         "peak_source": f"bf16_tflops_sustained ({peak_src})",
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_launches / args.steps,
-                         "kernel_share_of_step": k_ms / total_ms if total_ms else None},
-            "work": {"matches_per_pair": stats["matches"] / max(1, stats["pairs"]), "inliers_per_pair": stats["inliers"] / max(1, stats["pairs"])},
+                         "kernel_share_of_step": k_ms / total_ms if total_ms else None,
+                         "note": "split-fp16 x3 products: tensor-pipe FLOPs are 3x the algorithmic FLOPs counted here (ceiling of frac = 0.33)"},
+            "work": {"matches_per_pair": stats["matches"] / max(1, stats["pairs"]), "inliers_per_pair": stats["inliers"] / max(1, stats["pairs"]),
+                     "mean_stop_layer": stats["stops"] / max(1, stats["pairs"]) if w["matcher"] == "lightglue" else None,
+                     "keypoints_per_frame": stats["keypoints"] / max(1, stats["frames"])},
+            "encoder_conv_frac": ((conv_flop / 1e12) / (conv_ms / 1e3)) / tf_peak if conv_ms > 0 else None,
             "extra": {"superpoint_detect_describe_images_per_sec_1gpu": detect_ips,
                       "encoder_conv_tflops": (conv_flop / 1e12) / (conv_ms / 1e3) if conv_ms > 0 else None,
-                      "encoder_conv_frac_of_measured_bf16": ((conv_flop / 1e12) / (conv_ms / 1e3)) / tf_peak if conv_ms > 0 else None,
-                      "note": "split-fp16 x3 products: tensor-pipe FLOPs are 3x the algorithmic FLOPs reported here"},
+                      "kernel_family_ms_per_step": family_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = best_cpu_threads(frames)
-            v, stages = cpu_sample(frames, cal, 2, cores)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
-                                    "sample": "oracle port (torch-CPU fp32 + cv2 USAC): 3 detections, 2 LightGlue pairs at 5000x5000 keypoints / 9 layers, "
-                                              "2 verifications; pairs/s = 1 / (t_detect/20 + t_match + t_verify)", "stages": stages}
+            line["cpu_baseline"] = cpu_baseline(wname, quick=True)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_strong(args):
+    """One fixed job through the real L2 seam: F frames, Sequential(lookahead 20) pairs, B200CorrespondenceGenerator (every rank
+    detects the images its pairs reference, matches its p mod world shard in batches of 8, all_gather_object of the results) followed by
+    B200TwoViewBatch over the same shard.  Wall-clock on rank 0 between two barriers; total work is fixed => "strong"."""
+    import torch
+    import torch.distributed as dist
+
+    from gtsfm_b200 import distributed as D, synthetic as syn
+    from gtsfm_b200.correspondence_generator import B200CorrespondenceGenerator
+    from gtsfm_b200.gtsfm_api import Image
+    from gtsfm_b200.two_view import B200TwoViewBatch
+
+    rank, world, local, dev = _setup_dist()
+    F, L = args.frames, 20
+    frames, cal = syn.synthetic_sequence(F, 480, 640, seed=77)
+    images = [Image(f) for f in frames]
+    graph = [(i, j) for i in range(F) for j in range(i + 1, min(F, i + L + 1))]  # sequential_retriever.py:57-59
+    gen = B200CorrespondenceGenerator(syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "bench"), max_keypoints=5000, device=local)
+    gen.generate_correspondences(None, images[:4], [(0, 1), (1, 2), (2, 3)])  # warm-up: contexts, workspaces, NCCL
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0 = time.perf_counter()
+    kps, matches = gen.generate_correspondences(None, images, graph)
+    t_corr = time.perf_counter() - t0
+    fe = gen._front_end()
+    mine = D.shard_pairs(graph, rank, world)
+    feats = gen.last_device_features
+    put = {p: torch.from_numpy(matches[p]).to(dev) for p in mine}
+    res = B200TwoViewBatch(fe, THR_PX).run(feats, mine, {i: cal for i in range(F)}, putative=put)
+    n_ok = sum(1 for r in res.values() if r.i2Ri1 is not None)
+    barrier()
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([wall, t_corr, float(len(feats)), float(n_ok)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, t_corr, det_total, ok_total = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+    else:
+        det_total, ok_total = float(len(feats)), float(n_ok)
+    if rank == 0:
+        cfg = config_of("vga_lightglue")
+        cfg["workload"] = (f"strong scaling: ONE job of {F} synthetic 640x480 frames, Sequential lookahead 20 = {len(graph)} pairs (BASELINE configs[3] shape; "
+                           f"F = 500 gives its 9 790-pair graph), B200CorrespondenceGenerator + B200TwoViewBatch, pairs sharded p mod world")
+        line = {
+            "metric": "image_pairs_per_sec", "value": len(graph) / wall, "unit": "pairs/s", "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "gpu_launches": int(fe.ctx.launch_count()),
+            "strong": {"pairs": len(graph), "frames": F, "wall_s": wall, "correspondence_s_max_rank": t_corr,
+                       "detections_summed_over_ranks": det_total, "detections_if_not_duplicated": F, "verified_pairs": ok_total,
+                       "limits": "every rank re-detects the images its shard references (p mod world touches ~all frames), and the final "
+                                 "all_gather_object pickles every (K, 2) match array to every rank"},
+        }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -367,11 +592,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="vga_lightglue", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=120, help="--scaling strong: frames of the fixed job (500 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the plugin-path leg (the line is then not a valid bench line)")
+    ap.add_argument("--lg-batch", type=int, default=0, help="experiments: pairs per lock-step LightGlue batch inside the library (0 = default)")
     args = ap.parse_args()
-    args.warmup_ref = min(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.scaling == "strong":
+        run_strong(args)
     else:
         run_cuda(args)
 

@@ -27,10 +27,12 @@ class B200CorrespondenceGenerator(_Base):
         self._sp, self._lg = superpoint_weights, lightglue_weights
         self._max_keypoints, self._device, self._cpu_semantics = max_keypoints, device, cpu_semantics
         self._fe: Optional[DeviceFrontEnd] = None
+        self.last_device_features: Dict[int, DeviceFeatures] = {}  # device-resident features of the last call (for the two-view seam)
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_fe"] = None
+        st["last_device_features"] = {}
         return st
 
     def _front_end(self) -> DeviceFrontEnd:
@@ -60,6 +62,7 @@ class B200CorrespondenceGenerator(_Base):
             chunk = mine[c0:c0 + 8]
             for (i1, i2), (m, _) in zip(chunk, fe.match_batch([(feats[i1], feats[i2]) for i1, i2 in chunk])):
                 local[(i1, i2)] = m.cpu().numpy()
+        self.last_device_features = feats
         matches = D.gather_pair_results(local)
         keypoints: List[Optional[Keypoints]] = [None] * len(images)
         for idx, f in feats.items():

@@ -8,14 +8,17 @@
 //
 // Schedule: one CTA per SM walks output tiles `blockIdx.x + i * gridDim.x` of the whole batch (problem-major, then row
 // tile, then column tile - concurrently running CTAs share the A row tile through L2):
-//   warp 0 (lane 0)  TMA producer: K chunks of consecutive tiles flow through one 3-stage ring without draining
+//   warp 0 (lane 0)  TMA producer: K chunks of consecutive tiles flow through one 2-stage ring (2 x 64 KB) without draining
 //   warp 1           TMEM allocator (512 columns = two accumulator sets of 2 x 128) + MMA issuer (warp-uniform issue, tc.cuh)
-//   warps 2-9        epilogue: wait acc_full[set] -> tcgen05.ld -> shared-memory transpose -> coalesced bias / scale / ReLU /
-//                    residual -> fp32 and / or split planes; the set is released (acc_empty) once its last column block is
-//                    in registers, so tile t's epilogue overlaps tile t + 1's MMAs.  Warp w owns TMEM lane quarter w % 4
-//                    (rows) and column half (w - 2) / 4.
-// Tile = 128 x 128: per 64-wide K chunk the tensor pipe needs 768 cycles for the three products, shared memory serves
-// 96 KB of operand reads + 64 KB of TMA writes; the 128 x 64 tile of round 1 moved 1.5x the bytes per FLOP.
+//   warps 2-17       epilogue, ONE 32 x 32 block of the tile each (TMEM lane quarter w % 4 = rows, column block (w - 2) / 4):
+//                    operands that do not depend on the accumulator (bias) are fetched first, then wait acc_full[set] ->
+//                    tcgen05.ld -> release the set (acc_empty) -> 128-bit stores into a padded transpose pad -> read back as
+//                    (row, 4 consecutive columns) per lane -> bias / scale / ReLU / residual -> 16-byte fp32 and 8-byte
+//                    plane stores (8 lanes cover 128 contiguous bytes of a row).  Tile t's epilogue overlaps tile t + 1's MMAs.
+// Tile = 128 x 128: per 64-wide K chunk the tensor pipe needs 768 cycles for the three products.  With K = 256 / 512 a
+// tile is only 3072 / 6144 tensor cycles for 16 384 outputs, so the EPILOGUE, not the operand traffic, paces the linears
+// (ncu, profiles/r02_gemm_ws.txt: round-2's first version with 8 epilogue warps and scalar stores spent 12.4 k cycles per
+// tile, tensor pipe 27 %); hence one block per warp, vector accesses and no exposed dependent global load.
 #pragma once
 #include "tma.cuh"
 
@@ -24,9 +27,11 @@ constexpr int GW_M = 128, GW_N = 128, GW_K = 64;
 constexpr int GW_A_BYTES = GW_M * GW_K * 2;  // 16 KB per plane
 constexpr int GW_B_BYTES = GW_N * GW_K * 2;  // 16 KB per plane
 constexpr int GW_STAGE_BYTES = 2 * GW_A_BYTES + 2 * GW_B_BYTES;  // 64 KB
-constexpr int GW_STAGES = 3;
-constexpr int GW_THREADS = 320;
-constexpr int GW_SCRATCH = 8 * 32 * 33 * 4;  // one 32 x 33 fp32 transpose pad per epilogue warp
+constexpr int GW_STAGES = 2;
+constexpr int GW_EPI_WARPS = 16;
+constexpr int GW_THREADS = 64 + 32 * GW_EPI_WARPS;  // producer warp + MMA warp + 16 epilogue warps
+constexpr int GW_PAD = 36;  // fp32 row pitch of the transpose pad: 16-byte aligned rows, conflict-free for 128-bit accesses
+constexpr int GW_SCRATCH = GW_EPI_WARPS * 32 * GW_PAD * 4;  // one 32 x 36 fp32 transpose pad per epilogue warp
 constexpr size_t GW_SMEM = GW_STAGES * GW_STAGE_BYTES + GW_SCRATCH + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmProblem {
@@ -34,6 +39,7 @@ struct GemmProblem {
   float* C;            // optional fp32 output, row-major [M][ldc]
   __half *Ch, *Cl;     // optional split output planes
   int M, N, ldc;
+  int vec4;      // outputs / residual may be accessed 16 bytes at a time (leading dimensions and bases 16-byte aligned)
   int tiles_n;   // ceil(N / 128)
   int tile_end;  // running total of tiles up to and including this problem
 };
@@ -74,7 +80,7 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
 
   if (t == 0) {
     for (int s = 0; s < GW_STAGES; ++s) tc::mbar_init(&full[s], 1), tc::mbar_init(&empty[s], 1);
-    for (int b = 0; b < 2; ++b) tc::mbar_init(&acc_full[b], 1), tc::mbar_init(&acc_empty[b], 8);
+    for (int b = 0; b < 2; ++b) tc::mbar_init(&acc_full[b], 1), tc::mbar_init(&acc_empty[b], GW_EPI_WARPS);
     tc::fence_mbar_init();
     tc::tma_prefetch_desc(&maps.bh[0]);
     tc::tma_prefetch_desc(&maps.bl[0]);
@@ -150,13 +156,14 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
       tc::umma_commit_w(&acc_full[b]);
     }
   } else {
-    // ===== epilogue warps =====
-    const int ew = warp - 2;                 // 0..7
+    // ===== epilogue warps: warp e owns ONE 32 x 32 block of every tile (rows = its TMEM lane quarter, column block e / 4) =====
+    const int ew = warp - 2;                 // 0..15
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int chalf = ew >> 2;               // 64-column half of the tile
-    float* scratch = scratch_all + ew * (32 * 33);
+    const int cb = ew >> 2;                  // 32-column block of the tile
+    float* scratch = scratch_all + ew * (32 * GW_PAD);
     const float scale = g.scale;
     const int relu = g.relu;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // read-back: 4 rows per pass, lane -> (row rsub, columns c4 .. c4 + 3)
     int it = 0;
     for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
       int z, m0, n0;
@@ -164,77 +171,97 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) k_gemm_ws(const __grid_c
       const GemmProblem& pb = g.p[z];
       const int M = pb.M, N = pb.N;
       const int b = it & 1;
+      const int mw = m0 + quarter * 32;
+      const int n = n0 + cb * 32 + c4;  // first of this lane's 4 columns
+      // operands that do not depend on the accumulator are fetched before the wait
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) bias4[j] = __ldg(g.bias + n + j);
+      }
+      const bool vec = pb.vec4 && n + 3 < N;  // 16-byte accesses allowed for this lane's chunk
       ok = tc::mbar_wait(&acc_full[b], (it >> 1) & 1) && ok;
       tc::fence_after_sync();
-      const uint32_t lane_base = tmem + b * (2 * GW_N) + ((uint32_t)(quarter * 32) << 16);
-      const int mw = m0 + quarter * 32;
-      const int rows = min(32, M - mw);
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = chalf * 64 + cc * 32;
-        {
-          float a0[32], a1[32];
-          tc::tmem_ld32(lane_base + c0, a0);
-          tc::tmem_ld32(lane_base + GW_N + c0, a1);
-          if (cc == 1) {  // this warp's share of the set is in registers
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = fmaf(a1[j], tc::LO_INV, a0[j]);
-        }
+      const uint32_t lane_base = tmem + b * (2 * GW_N) + ((uint32_t)(quarter * 32) << 16) + cb * 32;
+      {
+        float a0[32], a1[32];
+        tc::tmem_ld32(lane_base, a0);
+        tc::tmem_ld32(lane_base + GW_N, a1);
+        tc::fence_before_sync();
         __syncwarp();
-        const int n = n0 + c0 + lane;
-        if (n < N && rows > 0) {
-          const float bn = g.bias ? g.bias[n] : 0.f;
-          const size_t off_h = ((size_t)(n >> 6) * M + mw) * 64 + (n & 63);
-          const size_t off_c = g.head_major ? off_h : (size_t)mw * pb.ldc + n;
-          const size_t off_s = g.head_major ? off_h : (size_t)mw * g.ldch + n;
-          const int str_c = g.head_major ? 64 : pb.ldc, str_s = g.head_major ? 64 : g.ldch;
-          const float* rp = pb.resid ? pb.resid + (size_t)mw * g.ldr + n : nullptr;
-          float* cp = pb.C ? pb.C + off_c : nullptr;
-          __half* hp = pb.Ch ? pb.Ch + off_s : nullptr;
-          __half* lp = pb.Ch ? pb.Cl + off_s : nullptr;
-          const float* sp = scratch + lane;
-          if (rp) {
-            float rv[32];
+        if (lane == 0) tc::mbar_arrive(&acc_empty[b]);  // this warp's share of the set is in registers
+        float4* dst = reinterpret_cast<float4*>(scratch + lane * GW_PAD);
 #pragma unroll
-            for (int r = 0; r < 32; ++r) rv[r] = r < rows ? rp[(size_t)r * g.ldr] : 0.f;
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_float4(fmaf(a1[4 * c], tc::LO_INV, a0[4 * c]), fmaf(a1[4 * c + 1], tc::LO_INV, a0[4 * c + 1]),
+                               fmaf(a1[4 * c + 2], tc::LO_INV, a0[4 * c + 2]), fmaf(a1[4 * c + 3], tc::LO_INV, a0[4 * c + 3]));
+      }
+      __syncwarp();
+      if (n < N) {
+        const size_t hm_col = (size_t)(n >> 6) * M * 64 + (n & 63);  // head-major: [N / 64][M][64]
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              if (r < rows) {
-                float v = (sp[r * 33] + bn) * scale;
-                if (relu) v = fmaxf(v, 0.f);
-                v += rv[r];
-                if (cp) cp[(size_t)r * str_c] = v;
-                if (hp) {
+        for (int ps = 0; ps < 8; ++ps) {
+          const int r = ps * 4 + rsub;
+          const int row = mw + r;
+          if (row >= M) break;  // rows ascend with ps: nothing further for this lane
+          const float4 x4 = *reinterpret_cast<const float4*>(scratch + r * GW_PAD + c4);
+          float v[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = (v[j] + bias4[j]) * scale;
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (pb.resid) {
+            const float* rp = pb.resid + (size_t)row * g.ldr + n;
+            if (vec) {
+              const float4 rr = *reinterpret_cast<const float4*>(rp);
+              v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < N) v[j] += rp[j];
+            }
+          }
+          const size_t off_c = g.head_major ? hm_col + (size_t)row * 64 : (size_t)row * pb.ldc + n;
+          const size_t off_s = g.head_major ? hm_col + (size_t)row * 64 : (size_t)row * g.ldch + n;
+          if (pb.C) {
+            if (vec) {
+              *reinterpret_cast<float4*>(pb.C + off_c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < N) pb.C[off_c + j] = v[j];
+            }
+          }
+          if (pb.Ch) {
+            if (vec) {
+              uint32_t h01, l01, h23, l23;
+              if (g.lo_unscaled) {
+                tc::split2_unscaled_clamped(v[0], v[1], h01, l01);
+                tc::split2_unscaled_clamped(v[2], v[3], h23, l23);
+              } else {
+                tc::split2(v[0], v[1], h01, l01);
+                tc::split2(v[2], v[3], h23, l23);
+              }
+              *reinterpret_cast<uint2*>(pb.Ch + off_s) = make_uint2(h01, h23);
+              *reinterpret_cast<uint2*>(pb.Cl + off_s) = make_uint2(l01, l23);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (n + j < N) {
                   __half hh, ll;
-                  if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
-                  else tc::split_h(v, hh, ll);
-                  hp[(size_t)r * str_s] = hh;
-                  lp[(size_t)r * str_s] = ll;
+                  if (g.lo_unscaled) tc::split_h_unscaled(v[j], hh, ll);
+                  else tc::split_h(v[j], hh, ll);
+                  pb.Ch[off_s + j] = hh;
+                  pb.Cl[off_s + j] = ll;
                 }
               }
             }
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < rows; ++r) {
-              float v = (sp[r * 33] + bn) * scale;
-              if (relu) v = fmaxf(v, 0.f);
-              if (cp) cp[(size_t)r * str_c] = v;
-              if (hp) {
-                __half hh, ll;
-                if (g.lo_unscaled) tc::split_h_unscaled(v, hh, ll);
-                else tc::split_h(v, hh, ll);
-                hp[(size_t)r * str_s] = hh;
-                lp[(size_t)r * str_s] = ll;
-              }
-            }
           }
         }
-        __syncwarp();  // scratch is reused by the next column block / tile
       }
+      __syncwarp();  // scratch is reused by the next tile
     }
   }
   __syncwarp();

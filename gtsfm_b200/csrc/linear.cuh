@@ -98,6 +98,13 @@ static int run_linear(b2_context* ctx, cudaStream_t st, const TcWeights& tw, con
     }
     GemmProblem& pr = q.p[nz];
     pr.resid = x.resid, pr.C = x.tc_want_f32 ? x.cf : nullptr, pr.Ch = x.cp.hi, pr.Cl = x.cp.lo, pr.M = x.M, pr.N = x.N, pr.ldc = x.ldc;
+    {  // 16-byte accesses in the epilogue need aligned bases and leading dimensions
+      auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+      const bool hm = x.head_major != 0;
+      bool v = al16(pr.resid) && (x.ldr % 4 == 0 || !pr.resid) && al16(pr.C) && (hm || x.ldc % 4 == 0 || !pr.C);
+      v = v && (reinterpret_cast<uintptr_t>(pr.Ch) & 7) == 0 && (reinterpret_cast<uintptr_t>(pr.Cl) & 7) == 0 && (hm || x.ldch % 4 == 0 || !pr.Ch);
+      pr.vec4 = v ? 1 : 0;
+    }
     pr.tiles_n = cdiv(x.N, GW_N);
     tiles += cdiv(x.M, GW_M) * pr.tiles_n;
     pr.tile_end = tiles;

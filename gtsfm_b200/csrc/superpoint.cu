@@ -270,89 +270,110 @@ __global__ void __launch_bounds__(128) k_head_scores(const float* __restrict__ c
 // simple_nms with radius 4 (superpoint.py:47-62), fused over a tile with a 20-pixel halo, followed by the
 // threshold + border test (superpoint.py:170-178) feeding per-row keypoint counts.
 constexpr int NT_W = 64, NT_H = 32, NR = 4, NHALO = 5 * NR;
-constexpr int NRW = NT_W + 2 * NHALO, NRH = NT_H + 2 * NHALO;  // 104 x 72
+constexpr int NRW = NT_W + 2 * NHALO, NRH = NT_H + 2 * NHALO;  // 104 x 72 region = tile + the 20-px halo the five pools need
 constexpr int NREG = NRW * NRH;
-
+// shared-memory planes carry a 4-cell sentinel frame (-inf for scores, 0 for masks) so that every 9-tap window is a fixed,
+// fully unrolled run of 9 loads with no bounds logic: pitch 112, 80 rows
+constexpr int NPW = NRW + 2 * NR, NPH = NRH + 2 * NR;
+constexpr int NPLANE = NPW * NPH;
+constexpr int NMS_THREADS = 1024;
+__device__ __forceinline__ int nms_idx(int c) {  // region cell c (row-major 104 x 72) -> index inside a padded plane
+  const int y = c / NRW, x = c - y * NRW;
+  return (y + NR) * NPW + x + NR;
+}
+// separable 9 x 9 max (F.max_pool2d(kernel 9, stride 1, padding 4), -inf padding) over the region
 __device__ __forceinline__ void pool9_f(const float* __restrict__ src, float* __restrict__ tmp, float* __restrict__ dst) {
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = i % NRW, y = i / NRW;
-    float m = -INFINITY;
-    int xa = max(x - NR, 0), xb = min(x + NR, NRW - 1);
-    for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, src[y * NRW + xx]);
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int i = nms_idx(c);
+    float m = src[i - 4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, src[i + d]);
     tmp[i] = m;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = i % NRW, y = i / NRW;
-    float m = -INFINITY;
-    int ya = max(y - NR, 0), yb = min(y + NR, NRH - 1);
-    for (int yy = ya; yy <= yb; ++yy) m = fmaxf(m, tmp[yy * NRW + x]);
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int i = nms_idx(c);
+    float m = tmp[i - 4 * NPW];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, tmp[i + d * NPW]);
     dst[i] = m;
   }
   __syncthreads();
 }
 __device__ __forceinline__ void dilate9_b(const uint8_t* __restrict__ src, uint8_t* __restrict__ tmp, uint8_t* __restrict__ dst) {
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = i % NRW, y = i / NRW;
-    uint8_t m = 0;
-    int xa = max(x - NR, 0), xb = min(x + NR, NRW - 1);
-    for (int xx = xa; xx <= xb; ++xx) m |= src[y * NRW + xx];
-    tmp[i] = m;
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int i = nms_idx(c);
+    unsigned m = src[i - 4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m |= src[i + d];
+    tmp[i] = (uint8_t)m;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = i % NRW, y = i / NRW;
-    uint8_t m = 0;
-    int ya = max(y - NR, 0), yb = min(y + NR, NRH - 1);
-    for (int yy = ya; yy <= yb; ++yy) m |= tmp[yy * NRW + x];
-    dst[i] = m;
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int i = nms_idx(c);
+    unsigned m = tmp[i - 4 * NPW];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m |= tmp[i + d * NPW];
+    dst[i] = (uint8_t)m;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_nms(const float* __restrict__ heat, float* __restrict__ nms, int H8, int W8,
-                                              float thr, int border, int* __restrict__ rowcnt) {
+// simple_nms(scores, 4) (superpoint.py:47-62) fused with the threshold / border test and the per-row survivor counts: one
+// pass over a 64 x 32 tile whose 20-px halo makes the three rounds of 9 x 9 pools local.  1024 threads (32 warps hide the
+// shared-memory latency of the unrolled 9-tap runs); float equality compares exactly as the reference does.
+__global__ void __launch_bounds__(NMS_THREADS) k_nms(const float* __restrict__ heat, float* __restrict__ nms, int H8, int W8,
+                                                      float thr, int border, int* __restrict__ rowcnt) {
   extern __shared__ __align__(16) unsigned char smraw[];
   float* S = reinterpret_cast<float*>(smraw);  // scores (-inf outside the image)
-  float* T = S + NREG;                         // scratch
-  float* X = T + NREG;                         // pooled scores
-  float* T2 = X + NREG;                        // scratch
-  uint8_t* M = reinterpret_cast<uint8_t*>(T2 + NREG);  // max_mask
-  uint8_t* P = M + NREG;                              // scratch
-  uint8_t* Q = P + NREG;                              // supp_mask
+  float* T = S + NPLANE;                       // suppressed scores
+  float* X = T + NPLANE;                       // pooled scores
+  float* T2 = X + NPLANE;                      // row-pass scratch
+  uint8_t* M = reinterpret_cast<uint8_t*>(T2 + NPLANE);  // max_mask
+  uint8_t* P = M + NPLANE;                               // scratch
+  uint8_t* Q = P + NPLANE;                               // supp_mask
   const int x0 = blockIdx.x * NT_W - NHALO, y0 = blockIdx.y * NT_H - NHALO;
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = x0 + i % NRW, y = y0 + i / NRW;
-    S[i] = (x >= 0 && x < W8 && y >= 0 && y < H8) ? heat[(size_t)y * W8 + x] : -INFINITY;
+  for (int i = threadIdx.x; i < NPLANE; i += NMS_THREADS) {  // sentinel frames (the region cells are overwritten below)
+    S[i] = -INFINITY, T[i] = -INFINITY, T2[i] = -INFINITY;
+    M[i] = 0, P[i] = 0;
   }
   __syncthreads();
-  pool9_f(S, T, X);
-  for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-    int x = x0 + i % NRW, y = y0 + i / NRW;
-    bool inside = (x >= 0 && x < W8 && y >= 0 && y < H8);
-    M[i] = (inside && S[i] == X[i]) ? 1 : 0;
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int ry = c / NRW, rx = c - ry * NRW;
+    const int x = x0 + rx, y = y0 + ry;
+    S[nms_idx(c)] = (x >= 0 && x < W8 && y >= 0 && y < H8) ? heat[(size_t)y * W8 + x] : -INFINITY;
+  }
+  __syncthreads();
+  pool9_f(S, T2, X);
+  for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+    const int i = nms_idx(c);
+    M[i] = (S[i] != -INFINITY && S[i] == X[i]) ? 1 : 0;  // (outside the image S = -inf: never a maximum)
   }
   __syncthreads();
   for (int it = 0; it < 2; ++it) {
     dilate9_b(M, P, Q);  // supp_mask = max_pool(max_mask) > 0
-    for (int i = threadIdx.x; i < NREG; i += blockDim.x) T[i] = Q[i] ? (S[i] == -INFINITY ? -INFINITY : 0.f) : S[i];
+    for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+      const int i = nms_idx(c);
+      T[i] = Q[i] ? (S[i] == -INFINITY ? -INFINITY : 0.f) : S[i];
+    }
     __syncthreads();
     pool9_f(T, T2, X);  // supp_scores in T, pooled into X
-    for (int i = threadIdx.x; i < NREG; i += blockDim.x) {
-      bool fresh = (T[i] == X[i]) && !Q[i] && S[i] != -INFINITY;
+    for (int c = threadIdx.x; c < NREG; c += NMS_THREADS) {
+      const int i = nms_idx(c);
+      const bool fresh = (T[i] == X[i]) && !Q[i] && S[i] != -INFINITY;
       M[i] = M[i] | (fresh ? 1 : 0);
     }
     __syncthreads();
   }
   // central tile: where(max_mask, scores, 0) + count survivors of threshold / border per row
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NT_W * NT_H; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NT_W * NT_H; i += NMS_THREADS) {
     int tx = i % NT_W, ty = i / NT_W;
     int x = blockIdx.x * NT_W + tx, y = blockIdx.y * NT_H + ty;
     bool inside = x < W8 && y < H8;
     float v = 0.f;
     if (inside) {
-      int r = (ty + NHALO) * NRW + tx + NHALO;
+      int r = (ty + NHALO + NR) * NPW + tx + NHALO + NR;
       v = M[r] ? S[r] : 0.f;
       nms[(size_t)y * W8 + x] = v;
     }
@@ -554,7 +575,7 @@ static int sp_conv3x3_tc(b2_context* ctx, cudaStream_t st, const DevBuf& in, int
   return B2_OK;
 }
 
-static size_t nms_smem_bytes() { return (size_t)NREG * 4 * sizeof(float) + (size_t)NREG * 3; }
+static size_t nms_smem_bytes() { return (size_t)NPLANE * 4 * sizeof(float) + (size_t)NPLANE * 3; }
 
 extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, size_t n_floats) {
   if (!ctx || !blob) return B2_ERR_ARG;
@@ -706,7 +727,7 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   B2_LAUNCH(ctx, k_head_scores, cdiv(Hc * Wc, PB_CELLS), 128, 0, st, head, s->w[9], s->b[9], s->heat.as<float>(), Hc, Wc);
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaMemsetAsync(s->rowcnt.p, 0, (size_t)(H8 + 1) * sizeof(int), st));
-  B2_LAUNCH(ctx, k_nms, dim3(cdiv(W8, NT_W), cdiv(H8, NT_H)), 256, nms_smem_bytes(), st, s->heat.as<float>(),
+  B2_LAUNCH(ctx, k_nms, dim3(cdiv(W8, NT_W), cdiv(H8, NT_H)), NMS_THREADS, nms_smem_bytes(), st, s->heat.as<float>(),
             s->nms.as<float>(), H8, W8, thr, border, s->rowcnt.as<int>());
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_scan_rows, 1, 1024, 0, st, s->rowcnt.as<int>(), s->rowoff.as<int>(), H8);

@@ -244,6 +244,10 @@ __device__ __forceinline__ void split2_unscaled(float a, float b, uint32_t& hi, 
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// unscaled lo plane with the range clamp of split2 (GEMM epilogues producing attention operands)
+__device__ __forceinline__ void split2_unscaled_clamped(float a, float b, uint32_t& hi, uint32_t& lo) {
+  split2_unscaled(clamp_h(a), clamp_h(b), hi, lo);
+}
 // ---- packed fp32 pairs (FFMA2 / FADD2: two IEEE fp32 operations per issue slot on sm_100) -----------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra, rb, rc, rd;

@@ -36,7 +36,7 @@ RESERVE_SMS_FOR_VERIFY = int(os.environ.get("B2_RESERVE_SMS", "8"))  # k_rs_hyp_
 
 class DeviceFrontEnd:
     def __init__(self, superpoint_sd, lightglue_sd=None, device: int = 0, max_keypoints: int = 5000, cpu_semantics: bool = True,
-                 ctx: Optional[_lib.Context] = None):
+                 ctx: Optional[_lib.Context] = None, superglue_sd=None):
         if not torch.cuda.is_available():
             raise _lib.B200Error("DeviceFrontEnd needs a CUDA device; there is no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -49,6 +49,9 @@ class DeviceFrontEnd:
         if lightglue_sd is not None:
             blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
             self.ctx.check(self.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
+        if superglue_sd is not None:
+            blob = weights.pack_superglue(weights.load_state_dict(superglue_sd))
+            self.ctx.check(self.lib.b2_superglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superglue_set_weights")
         # verification runs on its own context + stream + host thread so that the (latency-bound, 16-CTA) RANSAC kernels of
         # pair p overlap the matcher kernels of pair p+1 (ctypes calls release the GIL)
         self._vctx: Optional[_lib.Context] = None
@@ -111,6 +114,17 @@ class DeviceFrontEnd:
                                              self._stream())
         self.ctx.check(rc, "lightglue_match_dev")
         return out[: k.value], stop.value
+
+    def match_superglue(self, a: DeviceFeatures, b: DeviceFeatures, sinkhorn_iters: int = 20, match_threshold: float = 0.2) -> torch.Tensor:
+        """SuperGlue on device-resident features -> (k, 2) int64 device tensor (rows (i, matches0[i]) ascending in i)."""
+        cap = max(1, min(len(a), len(b)))
+        out = torch.empty((cap, 2), dtype=torch.int32, device=self.device)  # the ABI writes uint32 rows
+        k = _lib.C.c_int(0)
+        rc = self.lib.b2_superglue_match_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(a.score), _lib.ptr(a.desc), len(a), a.shape[0], a.shape[1],
+                                             _lib.ptr(b.kp), _lib.ptr(b.score), _lib.ptr(b.desc), len(b), b.shape[0], b.shape[1],
+                                             int(sinkhorn_iters), float(match_threshold), _lib.ptr(out), None, _lib.C.byref(k), self._stream())
+        self.ctx.check(rc, "superglue_match_dev")
+        return out[: k.value].to(torch.int64)
 
     def match_batch(self, pairs: Sequence[Tuple[DeviceFeatures, DeviceFeatures]], depth_confidence=0.95, width_confidence=0.99,
                     filter_threshold=0.1) -> List[Tuple[torch.Tensor, int]]:
