@@ -19,8 +19,9 @@ using namespace rmath;
 namespace {
 constexpr int RS_MAX_SOL = 10;
 constexpr int RS_SCORE_THREADS = 128;
-constexpr int RS_LO_THREADS = 256;
-constexpr int RS_LO_ITERS = 4;
+constexpr int RS_LO_THREADS = 512;
+constexpr int RS_LO_ITERS = 6;
+constexpr int RS_TOP = 8;  // hypotheses handed to the local optimisation (the refined candidate with the lowest MSAC cost wins)
 }  // namespace
 
 struct RansacState {
@@ -53,7 +54,8 @@ __device__ __forceinline__ double rs_err(int mode, const double* M, double a, do
 // ---- hypothesis generation -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_rs_hyp_E(const double* __restrict__ x1, const double* __restrict__ x2, int k,
                                                   unsigned long long seed, int sample0, int n_samples,
-                                                  double* __restrict__ models, int* __restrict__ nsol) {
+                                                  double* __restrict__ models, int* __restrict__ nsol, const int* __restrict__ go) {
+  if (go && !*go) return;  // extension stage not needed (decided on the device by k_rs_select)
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_samples) return;
   int idx[5];
@@ -123,7 +125,8 @@ __global__ void __launch_bounds__(64) k_rs_hyp_F(const double* __restrict__ x1, 
 __global__ void __launch_bounds__(RS_SCORE_THREADS) k_rs_score(const double* __restrict__ models, const int* __restrict__ nsol,
                                                                 const double* __restrict__ x1, const double* __restrict__ x2,
                                                                 int k, double thr2, int mode, double* __restrict__ cost,
-                                                                int* __restrict__ ninl) {
+                                                                int* __restrict__ ninl, const int* __restrict__ go) {
+  if (go && !*go) return;
   const int slot = blockIdx.x, s = slot / RS_MAX_SOL, j = slot % RS_MAX_SOL;
   if (j >= nsol[s]) {
     if (threadIdx.x == 0) cost[slot] = 1e300, ninl[slot] = 0;
@@ -158,32 +161,89 @@ __global__ void __launch_bounds__(RS_SCORE_THREADS) k_rs_score(const double* __r
   }
 }
 
-// ---- selection: arg-min MSAC cost over this batch, merged into the running best (ties -> lower slot) -------------
+// ---- selection: the RS_TOP lowest MSAC costs of this batch merged with the running candidate list (ties -> lower slot) ----
+// cand[0 .. RS_TOP) is kept sorted by (cost, arrival); each round is one block arg-min over the slots that come after the
+// previous winner in (cost, index) order.  A contaminated sample (4 of 5 inliers) usually scores close to the best one and
+// converges to the right model under the local optimisation, which is what makes few hypotheses enough at 30 % inliers.
 __global__ void __launch_bounds__(1024) k_rs_select(const double* __restrict__ models, const double* __restrict__ cost,
-                                                     const int* __restrict__ ninl, int n_slots, RsBest* __restrict__ best) {
+                                                     const int* __restrict__ ninl, int n_slots, RsBest* __restrict__ cand,
+                                                     const int* __restrict__ go, int* __restrict__ more, int k, int msize,
+                                                     double log_1mc, double done_after) {
+  if (go && !*go) return;
   __shared__ double sc[1024];
   __shared__ int si[1024];
-  double bc = 1e300;
-  int bi = -1;
-  for (int i = threadIdx.x; i < n_slots; i += 1024)
-    if (cost[i] < bc) bc = cost[i], bi = i;
-  sc[threadIdx.x] = bc, si[threadIdx.x] = bi;
+  __shared__ RsBest merged[RS_TOP];
+  __shared__ double prev_c;
+  __shared__ int prev_i;
+  // virtual slot index of an existing candidate j: -(RS_TOP - j) < 0, i.e. earlier arrivals win ties against this batch
+  if (threadIdx.x == 0) prev_c = -1.0, prev_i = -1000000;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      double oc = sc[threadIdx.x + o];
-      int oi = si[threadIdx.x + o];
-      if (oi >= 0 && (oc < sc[threadIdx.x] || (oc == sc[threadIdx.x] && (si[threadIdx.x] < 0 || oi < si[threadIdx.x]))))
-        sc[threadIdx.x] = oc, si[threadIdx.x] = oi;
+  for (int round = 0; round < RS_TOP; ++round) {
+    double bc = 1e300;
+    int bi = 0x7fffffff;
+    const double pc = prev_c;
+    const int pi = prev_i;
+    auto after_prev = [&](double c, int i) { return c > pc || (c == pc && i > pi); };
+    auto better = [&](double c, int i) { return c < bc || (c == bc && i < bi); };
+    for (int i = threadIdx.x; i < n_slots; i += 1024) {
+      const double c = cost[i];
+      if (c < 1e299 && after_prev(c, i) && better(c, i)) bc = c, bi = i;
+    }
+    if (threadIdx.x < RS_TOP && cand[threadIdx.x].valid) {
+      const double c = cand[threadIdx.x].cost;
+      const int i = (int)threadIdx.x - RS_TOP;
+      if (after_prev(c, i) && better(c, i)) bc = c, bi = i;
+    }
+    sc[threadIdx.x] = bc, si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const double oc = sc[threadIdx.x + o];
+        const int oi = si[threadIdx.x + o];
+        if (oc < sc[threadIdx.x] || (oc == sc[threadIdx.x] && oi < si[threadIdx.x])) sc[threadIdx.x] = oc, si[threadIdx.x] = oi;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      RsBest& m = merged[round];
+      if (si[0] == 0x7fffffff) {
+        m.valid = 0, m.cost = 1e300, m.ninl = 0;
+        prev_c = 1e300, prev_i = 0x7fffffff;
+      } else {
+        if (si[0] < 0) {
+          m = cand[si[0] + RS_TOP];
+        } else {
+          for (int i = 0; i < 9; ++i) m.model[i] = models[(size_t)si[0] * 9 + i];
+          m.cost = sc[0], m.ninl = ninl[si[0]], m.valid = 1;
+        }
+        prev_c = sc[0], prev_i = si[0];
+      }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && si[0] >= 0 && sc[0] < 1e299 && (!best->valid || sc[0] < best->cost)) {
-    for (int i = 0; i < 9; ++i) best->model[i] = models[(size_t)si[0] * 9 + i];
-    best->cost = sc[0];
-    best->ninl = ninl[si[0]];
-    best->valid = 1;
+  if (threadIdx.x < RS_TOP) cand[threadIdx.x] = merged[threadIdx.x];
+  if (threadIdx.x == 0 && more) {
+    // standard RANSAC bound with the support of the best hypothesis so far: are `done_after` samples enough for the requested
+    // confidence?  If not, the (already enqueued) extension stage runs; otherwise its kernels return at once.
+    int need_more = 1;
+    if (merged[0].valid) {
+      const double w = (double)merged[0].ninl / (double)k;
+      const double pw = pow(w, (double)msize);
+      const double need = pw >= 1.0 ? 1.0 : (pw <= 0.0 ? 1e300 : log_1mc / log(1.0 - pw));
+      need_more = need > done_after ? 1 : 0;
+    }
+    *more = need_more;
   }
+}
+
+// after the local optimisation: the refined candidate with the lowest cost (ties -> lower rank) becomes the result
+__global__ void k_rs_pick(const RsBest* __restrict__ cand, RsBest* __restrict__ best) {
+  if (threadIdx.x != 0) return;
+  int b = -1;
+  for (int j = 0; j < RS_TOP; ++j)
+    if (cand[j].valid && (b < 0 || cand[j].cost < cand[b].cost)) b = j;
+  if (b >= 0) *best = cand[b];
+  else best->valid = 0, best->cost = 1e300, best->ninl = 0;
 }
 
 // ---- local optimisation: iterated normalised least-squares refit on the current inliers --------------------------
@@ -198,34 +258,112 @@ __device__ double block_sum(double v, double* sh) {
   return t;
 }
 
+// Jacobi eigen-decomposition of a symmetric 9 x 9 matrix in SHARED memory by one warp, parallel (round-robin) ordering:
+// each of the 9 rounds of a sweep applies FOUR rotations on disjoint index pairs at once - their angles come from lanes
+// 0..3, the 4 x 9 two-element column updates of A and V and then the 4 x 9 row updates of A are spread over the lanes.
+// Disjoint rotations commute, so a round equals the same four rotations applied one after the other.  A single thread
+// walking the run-time indexed matrix in local memory (rmath::jacobi_eig<9>) took ~45 us per call on B200.
+__device__ void jacobi9_warp(double* A, double* V, int lane) {
+  __shared__ double rc[4], rs[4];
+  __shared__ int rp[4], rq[4];
+  for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = lane; i < 81; i += 32) {
+      const double v = A[i] * A[i];
+      if (i / 9 == i % 9) diag += v;
+      else off += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o), diag += __shfl_xor_sync(0xffffffffu, diag, o);
+    if (0.5 * off <= 1e-26 * (diag + 1e-300)) break;
+    for (int r = 0; r < 9; ++r) {  // circle method over 10 players, player 9 is a bye: pairs ((r + i) % 9, (r - i) % 9), i = 1..4
+      if (lane < 4) {
+        const int a = (r + lane + 1) % 9, b = (r + 9 - lane - 1) % 9;
+        const int pp = a < b ? a : b, qq = a < b ? b : a;
+        const double apq = A[pp * 9 + qq];
+        double c = 1.0, sn = 0.0;
+        if (fabs(apq) >= 1e-300) {
+          const double theta = (A[qq * 9 + qq] - A[pp * 9 + pp]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        }
+        rc[lane] = c, rs[lane] = sn, rp[lane] = pp, rq[lane] = qq;
+      }
+      __syncwarp();
+      for (int it = lane; it < 36; it += 32) {  // columns p, q of A and of V, row k
+        const int i = it / 9, k = it - i * 9;
+        const double c = rc[i], sn = rs[i];
+        const int pp = rp[i], qq = rq[i];
+        const double akp = A[k * 9 + pp], akq = A[k * 9 + qq];
+        A[k * 9 + pp] = c * akp - sn * akq;
+        A[k * 9 + qq] = sn * akp + c * akq;
+        const double vkp = V[k * 9 + pp], vkq = V[k * 9 + qq];
+        V[k * 9 + pp] = c * vkp - sn * vkq;
+        V[k * 9 + qq] = sn * vkp + c * vkq;
+      }
+      __syncwarp();
+      for (int it = lane; it < 36; it += 32) {  // rows p, q of A, column k
+        const int i = it / 9, k = it - i * 9;
+        const double c = rc[i], sn = rs[i];
+        const int pp = rp[i], qq = rq[i];
+        const double apk = A[pp * 9 + k], aqk = A[qq * 9 + k];
+        A[pp * 9 + k] = c * apk - sn * aqk;
+        A[qq * 9 + k] = sn * apk + c * aqk;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RS_LO_THREADS) k_rs_refine(const double* __restrict__ x1, const double* __restrict__ x2, int k,
-                                                              double thr2, int mode, RsBest* __restrict__ best) {
+                                                              double thr2, int mode, RsBest* __restrict__ cands) {
+  RsBest* best = cands + blockIdx.x;  // one CTA per candidate
   __shared__ double sh[RS_LO_THREADS / 32];
   __shared__ double M[9], cand[9];
   __shared__ double mom[45];
   __shared__ double part[RS_LO_THREADS / 32][45];
+  __shared__ double JA[81], JV[81];
   if (!best->valid) return;
   if (threadIdx.x < 9) M[threadIdx.x] = best->model[threadIdx.x];
   __syncthreads();
   double cur_cost = best->cost;
   const int min_pts = 8;
   for (int it = 0; it < RS_LO_ITERS; ++it) {
-    // centroids and mean distances of the inliers under M (Hartley normalisation)
+    // The support set of the first refits is taken with a WIDER threshold (4x, 2x the squared threshold): a hypothesis
+    // from a slightly contaminated sample holds only part of the true inliers within thr, and a least-squares refit on
+    // that part stays biased; acceptance is always judged by the MSAC cost at the real threshold.
+    const double sel2 = thr2 * (it == 0 ? 4.0 : (it == 1 ? 2.0 : 1.0));
+    // inlier flags of this thread's points under M, evaluated once per iteration (bit j <-> point threadIdx.x + j * T)
+    unsigned long long flags = 0ull;
     double a[5] = {0, 0, 0, 0, 0};
-    for (int i = threadIdx.x; i < k; i += RS_LO_THREADS) {
-      double e = rs_err(mode, M, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
-      if (e < thr2) a[0] += x1[2 * i], a[1] += x1[2 * i + 1], a[2] += x2[2 * i], a[3] += x2[2 * i + 1], a[4] += 1.0;
+    {
+      int j = 0;
+      for (int i = threadIdx.x; i < k; i += RS_LO_THREADS, ++j) {
+        const double e = rs_err(mode, M, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
+        if (e < sel2) {
+          if (j < 64) flags |= 1ull << j;
+          a[0] += x1[2 * i], a[1] += x1[2 * i + 1], a[2] += x2[2 * i], a[3] += x2[2 * i + 1], a[4] += 1.0;
+        }
+      }
     }
+    auto is_in = [&](int i, int j) {  // beyond 64 points per thread (k > 32768) fall back to re-evaluation
+      return j < 64 ? ((flags >> j) & 1ull) != 0 : rs_err(mode, M, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]) < sel2;
+    };
+    // centroids and mean distances of the inliers under M (Hartley normalisation)
     double cnt = block_sum(a[4], sh);
     if (cnt < min_pts) break;
     double c1x = block_sum(a[0], sh) / cnt, c1y = block_sum(a[1], sh) / cnt, c2x = block_sum(a[2], sh) / cnt,
            c2y = block_sum(a[3], sh) / cnt;
     double d1 = 0, d2 = 0;
-    for (int i = threadIdx.x; i < k; i += RS_LO_THREADS) {
-      double e = rs_err(mode, M, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
-      if (e < thr2) {
-        d1 += sqrt((x1[2 * i] - c1x) * (x1[2 * i] - c1x) + (x1[2 * i + 1] - c1y) * (x1[2 * i + 1] - c1y));
-        d2 += sqrt((x2[2 * i] - c2x) * (x2[2 * i] - c2x) + (x2[2 * i + 1] - c2y) * (x2[2 * i + 1] - c2y));
+    {
+      int j = 0;
+      for (int i = threadIdx.x; i < k; i += RS_LO_THREADS, ++j) {
+        if (is_in(i, j)) {
+          d1 += sqrt((x1[2 * i] - c1x) * (x1[2 * i] - c1x) + (x1[2 * i + 1] - c1y) * (x1[2 * i + 1] - c1y));
+          d2 += sqrt((x2[2 * i] - c2x) * (x2[2 * i] - c2x) + (x2[2 * i + 1] - c2y) * (x2[2 * i + 1] - c2y));
+        }
       }
     }
     d1 = block_sum(d1, sh), d2 = block_sum(d2, sh);
@@ -235,17 +373,19 @@ __global__ void __launch_bounds__(RS_LO_THREADS) k_rs_refine(const double* __res
     double acc[45];
 #pragma unroll
     for (int i = 0; i < 45; ++i) acc[i] = 0;
-    for (int i = threadIdx.x; i < k; i += RS_LO_THREADS) {
-      double e = rs_err(mode, M, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
-      if (e < thr2) {
-        double ax = (x1[2 * i] - c1x) * s1, ay = (x1[2 * i + 1] - c1y) * s1;
-        double bx = (x2[2 * i] - c2x) * s2, by = (x2[2 * i + 1] - c2y) * s2;
-        double q[9] = {bx * ax, bx * ay, bx, by * ax, by * ay, by, ax, ay, 1.0};
-        int t = 0;
+    {
+      int j = 0;
+      for (int i = threadIdx.x; i < k; i += RS_LO_THREADS, ++j) {
+        if (is_in(i, j)) {
+          double ax = (x1[2 * i] - c1x) * s1, ay = (x1[2 * i + 1] - c1y) * s1;
+          double bx = (x2[2 * i] - c2x) * s2, by = (x2[2 * i + 1] - c2y) * s2;
+          double q[9] = {bx * ax, bx * ay, bx, by * ax, by * ay, by, ax, ay, 1.0};
+          int t = 0;
 #pragma unroll
-        for (int r = 0; r < 9; ++r)
+          for (int r = 0; r < 9; ++r)
 #pragma unroll
-          for (int c = r; c < 9; ++c) acc[t++] += q[r] * q[c];
+            for (int c = r; c < 9; ++c) acc[t++] += q[r] * q[c];
+        }
       }
     }
 #pragma unroll
@@ -262,23 +402,32 @@ __global__ void __launch_bounds__(RS_LO_THREADS) k_rs_refine(const double* __res
       mom[threadIdx.x] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double A[81];
-      int t = 0;
-      for (int r = 0; r < 9; ++r)
-        for (int c = r; c < 9; ++c) A[r * 9 + c] = A[c * 9 + r] = mom[t++];
-      double Fn[9];
-      smallest_eigvec9(A, Fn);
-      double T1[9] = {s1, 0, -s1 * c1x, 0, s1, -s1 * c1y, 0, 0, 1}, T2t[9] = {s2, 0, 0, 0, s2, 0, -s2 * c2x, -s2 * c2y, 1};
-      double tmp[9], F[9];
-      mat3_mul(T2t, Fn, tmp);
-      mat3_mul(tmp, T1, F);
-      if (mode == 0) enforce_essential(F);
-      else enforce_rank2(F);
-      double n = 0;
-      for (int i = 0; i < 9; ++i) n += F[i] * F[i];
-      n = sqrt(n);
-      for (int i = 0; i < 9; ++i) cand[i] = n > 1e-300 ? F[i] / n : 0.0;
+    if (threadIdx.x < 32) {  // warp 0: smallest eigenvector of the moment matrix -> candidate model
+      if (threadIdx.x == 0) {
+        int t = 0;
+        for (int r = 0; r < 9; ++r)
+          for (int c = r; c < 9; ++c) JA[r * 9 + c] = JA[c * 9 + r] = mom[t++];
+      }
+      __syncwarp();
+      jacobi9_warp(JA, JV, threadIdx.x);
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        int kk = 0;
+        for (int i = 1; i < 9; ++i)
+          if (JA[i * 9 + i] < JA[kk * 9 + kk]) kk = i;
+        double Fn[9];
+        for (int i = 0; i < 9; ++i) Fn[i] = JV[i * 9 + kk];
+        double T1[9] = {s1, 0, -s1 * c1x, 0, s1, -s1 * c1y, 0, 0, 1}, T2t[9] = {s2, 0, 0, 0, s2, 0, -s2 * c2x, -s2 * c2y, 1};
+        double tmp[9], F[9];
+        mat3_mul(T2t, Fn, tmp);
+        mat3_mul(tmp, T1, F);
+        if (mode == 0) enforce_essential(F);
+        else enforce_rank2(F);
+        double n = 0;
+        for (int i = 0; i < 9; ++i) n += F[i] * F[i];
+        n = sqrt(n);
+        for (int i = 0; i < 9; ++i) cand[i] = n > 1e-300 ? F[i] / n : 0.0;
+      }
     }
     __syncthreads();
     double c = 0, ni = 0;
@@ -289,7 +438,10 @@ __global__ void __launch_bounds__(RS_LO_THREADS) k_rs_refine(const double* __res
     }
     c = block_sum(c, sh);
     ni = block_sum(ni, sh);
-    if (!(c < cur_cost)) break;  // no improvement: keep M
+    if (!(c < cur_cost)) {  // no improvement: keep M (the wide-threshold rounds get their narrower successors first)
+      if (it >= 2) break;
+      continue;
+    }
     cur_cost = c;
     __syncthreads();
     if (threadIdx.x < 9) M[threadIdx.x] = cand[threadIdx.x];
@@ -311,25 +463,28 @@ __global__ void __launch_bounds__(256) k_rs_mask(const double* __restrict__ x1, 
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
 
-// ---- pose recovery (cv2.recoverPose semantics): single CTA, votes over the masked points ---------------------------
-__global__ void __launch_bounds__(256) k_rs_pose(const double* __restrict__ E, const double* __restrict__ x1,
-                                                  const double* __restrict__ x2, const uint8_t* __restrict__ mask, int k,
-                                                  double* __restrict__ out /*R[9], t[3], good*/) {
+// ---- pose recovery (cv2.recoverPose semantics): one correspondence per thread, integer votes, last CTA decides ------
+constexpr int RS_POSE_THREADS = 128;
+__global__ void __launch_bounds__(RS_POSE_THREADS) k_rs_pose(const double* __restrict__ E, const double* __restrict__ x1,
+                                                              const double* __restrict__ x2, const uint8_t* __restrict__ mask, int k,
+                                                              int* __restrict__ gvotes /*[4] votes + [1] CTA counter, zero on entry*/,
+                                                              double* __restrict__ out /*R[9], t[3], good*/) {
   __shared__ double R1[9], R2[9], t[3];
   __shared__ int votes[4];
+  __shared__ int is_last;
   if (threadIdx.x == 0) {
     decompose_E(E, R1, R2, t);
     votes[0] = votes[1] = votes[2] = votes[3] = 0;
   }
   __syncthreads();
   int v[4] = {0, 0, 0, 0};
-  for (int i = threadIdx.x; i < k; i += 256) {
-    if (mask && !mask[i]) continue;
-    double tn[3] = {-t[0], -t[1], -t[2]};
-    v[0] += cheirality_ok(R1, t, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
-    v[1] += cheirality_ok(R2, t, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
-    v[2] += cheirality_ok(R1, tn, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
-    v[3] += cheirality_ok(R2, tn, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
+  const int i = blockIdx.x * RS_POSE_THREADS + threadIdx.x;
+  if (i < k && (!mask || mask[i])) {
+    const double tn[3] = {-t[0], -t[1], -t[2]};
+    v[0] = cheirality_ok(R1, t, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
+    v[1] = cheirality_ok(R2, t, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
+    v[2] = cheirality_ok(R1, tn, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
+    v[3] = cheirality_ok(R2, tn, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], 50.0);
   }
   for (int c = 0; c < 4; ++c) {
     int s = v[c];
@@ -339,14 +494,24 @@ __global__ void __launch_bounds__(256) k_rs_pose(const double* __restrict__ E, c
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    for (int c = 0; c < 4; ++c)
+      if (votes[c]) atomicAdd(&gvotes[c], votes[c]);
+    __threadfence();
+    is_last = atomicAdd(&gvotes[4], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    int tot[4];
+    for (int c = 0; c < 4; ++c) tot[c] = *reinterpret_cast<volatile int*>(&gvotes[c]);
     int b = 0;
     for (int c = 1; c < 4; ++c)
-      if (votes[c] > votes[b]) b = c;  // ties -> first, in cv2's order (R1,t), (R2,t), (R1,-t), (R2,-t)
+      if (tot[c] > tot[b]) b = c;  // ties -> first, in cv2's order (R1,t), (R2,t), (R1,-t), (R2,-t)
     const double* R = (b & 1) ? R2 : R1;
     double sg = (b & 2) ? -1.0 : 1.0;
-    for (int i = 0; i < 9; ++i) out[i] = R[i];
-    for (int i = 0; i < 3; ++i) out[9 + i] = sg * t[i];
-    out[12] = (double)votes[b];
+    for (int j = 0; j < 9; ++j) out[j] = R[j];
+    for (int j = 0; j < 3; ++j) out[9 + j] = sg * t[j];
+    out[12] = (double)tot[b];
   }
 }
 
@@ -384,7 +549,7 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
   if (k < m) return 1;
   const int hard_cap = mode == 0 ? 65536 : 262144;
   const int max_iters = prm->max_iters < 1 ? 1 : (prm->max_iters > hard_cap ? hard_cap : prm->max_iters);
-  const int batch = max_iters < 16384 ? max_iters : 16384;
+  const int batch = 16384;  // hypotheses per launch (buffers are sized for it)
   const double thr2 = prm->threshold * prm->threshold;
   B2_CUDA(ctx, s->x1.ensure((size_t)k * 16));
   B2_CUDA(ctx, s->x2.ensure((size_t)k * 16));
@@ -392,17 +557,18 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
   B2_CUDA(ctx, s->nsol.ensure((size_t)batch * 4));
   B2_CUDA(ctx, s->cost.ensure((size_t)batch * RS_MAX_SOL * 8));
   B2_CUDA(ctx, s->ninl.ensure((size_t)batch * RS_MAX_SOL * 4));
-  B2_CUDA(ctx, s->best.ensure(sizeof(RsBest) + 16));
+  B2_CUDA(ctx, s->best.ensure(sizeof(RsBest) * (1 + RS_TOP) + 16));  // [0] result, then the counter, then the RS_TOP candidates
   B2_CUDA(ctx, s->mask.ensure((size_t)k + 16));
-  B2_CUDA(ctx, s->pose.ensure(16 * 8));
+  B2_CUDA(ctx, s->pose.ensure(48 * 8));  // [0,13) R, t, votes of the winner | [16,25) E (recover_pose) | [32,..) int votes[4] + counter
   B2_CUDA(ctx, s->hbuf.ensure(sizeof(RsBest) + 16 * 8 + 64));
   if (hx1) {
     B2_CUDA(ctx, cudaMemcpyAsync(s->x1.p, hx1, (size_t)k * 16, cudaMemcpyHostToDevice, st));
     B2_CUDA(ctx, cudaMemcpyAsync(s->x2.p, hx2, (size_t)k * 16, cudaMemcpyHostToDevice, st));
   }
-  B2_CUDA(ctx, cudaMemsetAsync(s->best.p, 0, sizeof(RsBest) + 16, st));
+  B2_CUDA(ctx, cudaMemsetAsync(s->best.p, 0, sizeof(RsBest) * (1 + RS_TOP) + 16, st));
   RsBest* dbest = s->best.as<RsBest>();
   int* dcount = reinterpret_cast<int*>(s->best.as<char>() + sizeof(RsBest));
+  RsBest* dcand = reinterpret_cast<RsBest*>(s->best.as<char>() + sizeof(RsBest) + 16);
   RsBest* hbest = s->hbuf.as<RsBest>();
   const double *x1 = s->x1.as<double>(), *x2 = s->x2.as<double>();
   int done = 0;
@@ -410,21 +576,21 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
     const int n = (max_iters - done) < batch ? (max_iters - done) : batch;
     if (mode == 0)
       B2_LAUNCH(ctx, k_rs_hyp_E, cdiv(n, 64), 64, 0, st, x1, x2, k, (unsigned long long)prm->seed, done, n,
-                s->models.as<double>(), s->nsol.as<int>());
+                s->models.as<double>(), s->nsol.as<int>(), (const int*)nullptr);
     else
       B2_LAUNCH(ctx, k_rs_hyp_F, cdiv(n, 64), 64, 0, st, x1, x2, k, (unsigned long long)prm->seed, done, n,
                 s->models.as<double>(), s->nsol.as<int>());
     B2_CHECK_LAUNCH(ctx);
     B2_LAUNCH(ctx, k_rs_score, n * RS_MAX_SOL, RS_SCORE_THREADS, 0, st, s->models.as<double>(), s->nsol.as<int>(), x1, x2, k,
-              thr2, mode, s->cost.as<double>(), s->ninl.as<int>());
+              thr2, mode, s->cost.as<double>(), s->ninl.as<int>(), (const int*)nullptr);
     B2_CHECK_LAUNCH(ctx);
     B2_LAUNCH(ctx, k_rs_select, 1, 1024, 0, st, s->models.as<double>(), s->cost.as<double>(), s->ninl.as<int>(),
-              n * RS_MAX_SOL, dbest);
+              n * RS_MAX_SOL, dcand, (const int*)nullptr, dcount + 1, k, m, log(1.0 - prm->confidence), (double)(done + n));
     B2_CHECK_LAUNCH(ctx);
     done += n;
     if (done >= max_iters) break;
     // adaptive termination (standard RANSAC bound) between batches
-    B2_CUDA(ctx, cudaMemcpyAsync(hbest, dbest, sizeof(RsBest), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(ctx, cudaMemcpyAsync(hbest, dcand, sizeof(RsBest), cudaMemcpyDeviceToHost, st));  // the best unrefined candidate
     B2_CUDA(ctx, cudaStreamSynchronize(st));
     if (hbest->valid) {
       double w = (double)hbest->ninl / k, pw = pow(w, m);
@@ -432,13 +598,35 @@ static int rs_run(b2_context* ctx, const double* hx1, const double* hx2, int k, 
       if ((double)done >= need) break;
     }
   }
-  B2_LAUNCH(ctx, k_rs_refine, 1, RS_LO_THREADS, 0, st, x1, x2, k, thr2, mode, dbest);
+  if (mode == 0 && done >= max_iters && max_iters <= 4096) {
+    // Extension stage (E only): cv2's budget of `max_iters` samples leaves a 30 %-inlier pair without a single uncontaminated
+    // 5-sample one time in eleven; USAC survives that through its graph-cut local optimisation, a plain RANSAC does not.  The
+    // hypothesis kernel is latency-bound, so 4x more samples cost about as much as the first batch; they only run when the
+    // confidence bound of the best model so far says `max_iters` were not enough (flag written by k_rs_select on the device).
+    const int n2 = 4 * max_iters < batch ? 4 * max_iters : batch;
+    const int* go = dcount + 1;
+    B2_LAUNCH(ctx, k_rs_hyp_E, cdiv(n2, 64), 64, 0, st, x1, x2, k, (unsigned long long)prm->seed, done, n2, s->models.as<double>(),
+              s->nsol.as<int>(), go);
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_rs_score, n2 * RS_MAX_SOL, RS_SCORE_THREADS, 0, st, s->models.as<double>(), s->nsol.as<int>(), x1, x2, k, thr2, mode,
+              s->cost.as<double>(), s->ninl.as<int>(), go);
+    B2_CHECK_LAUNCH(ctx);
+    B2_LAUNCH(ctx, k_rs_select, 1, 1024, 0, st, s->models.as<double>(), s->cost.as<double>(), s->ninl.as<int>(), n2 * RS_MAX_SOL, dcand, go,
+              (int*)nullptr, k, m, 0.0, 0.0);
+    B2_CHECK_LAUNCH(ctx);
+  }
+  B2_LAUNCH(ctx, k_rs_refine, RS_TOP, RS_LO_THREADS, 0, st, x1, x2, k, thr2, mode, dcand);
+  B2_CHECK_LAUNCH(ctx);
+  B2_LAUNCH(ctx, k_rs_pick, 1, 32, 0, st, dcand, dbest);
   B2_CHECK_LAUNCH(ctx);
   B2_LAUNCH(ctx, k_rs_mask, cdiv(k, 256), 256, 0, st, x1, x2, k, thr2, mode, dbest, s->mask.as<uint8_t>(), dcount);
   B2_CHECK_LAUNCH(ctx);
   const bool want_pose = mode == 0 && out_R && out_t;
   if (want_pose) {
-    B2_LAUNCH(ctx, k_rs_pose, 1, 256, 0, st, dbest->model, x1, x2, s->mask.as<uint8_t>(), k, s->pose.as<double>());
+    int* gvotes = reinterpret_cast<int*>(s->pose.as<double>() + 32);
+    B2_CUDA(ctx, cudaMemsetAsync(gvotes, 0, 8 * sizeof(int), st));
+    B2_LAUNCH(ctx, k_rs_pose, cdiv(k, RS_POSE_THREADS), RS_POSE_THREADS, 0, st, dbest->model, x1, x2, s->mask.as<uint8_t>(), k, gvotes,
+              s->pose.as<double>());
     B2_CHECK_LAUNCH(ctx);
   }
   char* hb = s->hbuf.as<char>();
@@ -512,7 +700,7 @@ extern "C" int b2_recover_pose_host(b2_context* ctx, const double* E, const doub
   cudaStream_t st = ctx->stream;
   B2_CUDA(ctx, s->x1.ensure((size_t)(k + 1) * 16));
   B2_CUDA(ctx, s->x2.ensure((size_t)(k + 1) * 16));
-  B2_CUDA(ctx, s->pose.ensure(32 * 8));
+  B2_CUDA(ctx, s->pose.ensure(48 * 8));
   B2_CUDA(ctx, s->hbuf.ensure(sizeof(RsBest) + 16 * 8 + 64));
   if (k > 0) {
     B2_CUDA(ctx, cudaMemcpyAsync(s->x1.p, x1, (size_t)k * 16, cudaMemcpyHostToDevice, st));
@@ -520,8 +708,12 @@ extern "C" int b2_recover_pose_host(b2_context* ctx, const double* E, const doub
   }
   double* dE = s->pose.as<double>() + 16;
   B2_CUDA(ctx, cudaMemcpyAsync(dE, E, 9 * 8, cudaMemcpyHostToDevice, st));
-  B2_LAUNCH(ctx, k_rs_pose, 1, 256, 0, st, dE, s->x1.as<double>(), s->x2.as<double>(), (const uint8_t*)nullptr, k,
-            s->pose.as<double>());
+  {
+    int* gvotes = reinterpret_cast<int*>(s->pose.as<double>() + 32);
+    B2_CUDA(ctx, cudaMemsetAsync(gvotes, 0, 8 * sizeof(int), st));
+    B2_LAUNCH(ctx, k_rs_pose, k > 0 ? cdiv(k, RS_POSE_THREADS) : 1, RS_POSE_THREADS, 0, st, dE, s->x1.as<double>(), s->x2.as<double>(),
+              (const uint8_t*)nullptr, k, gvotes, s->pose.as<double>());
+  }
   B2_CHECK_LAUNCH(ctx);
   double* h = s->hbuf.as<double>();
   B2_CUDA(ctx, cudaMemcpyAsync(h, s->pose.p, 13 * 8, cudaMemcpyDeviceToHost, st));

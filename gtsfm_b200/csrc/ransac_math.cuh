@@ -21,6 +21,14 @@ namespace rmath {
 // ---- small dense linear algebra -----------------------------------------------------------------------------------
 
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major, destroyed).  V columns = eigenvectors.
+// On the device the rotation loops of the small instances (N <= 4: svd3, the cheirality triangulation) are fully unrolled,
+// so every index is static and A / V stay in registers; with run-time (p, q) they live in local memory and each of the
+// ~200 accesses per rotation is a dependent L1 round trip - that, not the arithmetic, is what made the fp64 kernels slow.
+#if defined(__CUDA_ARCH__)
+#define RM_UNROLL_SMALL _Pragma("unroll")
+#else
+#define RM_UNROLL_SMALL
+#endif
 template <int N>
 RM_HDN void jacobi_eig(double* A, double* V, double* w) {
   for (int i = 0; i < N; ++i)
@@ -32,6 +40,38 @@ RM_HDN void jacobi_eig(double* A, double* V, double* w) {
       for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
     }
     if (off <= 1e-30 * (diag + 1e-300)) break;
+    if (N <= 4) {
+      RM_UNROLL_SMALL
+      for (int p = 0; p < N - 1; ++p) {
+        RM_UNROLL_SMALL
+        for (int q = p + 1; q < N; ++q) {
+          double apq = A[p * N + q];
+          if (fabs(apq) < 1e-300) continue;
+          double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+          double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+          RM_UNROLL_SMALL
+          for (int k = 0; k < N; ++k) {
+            double akp = A[k * N + p], akq = A[k * N + q];
+            A[k * N + p] = c * akp - s * akq;
+            A[k * N + q] = s * akp + c * akq;
+          }
+          RM_UNROLL_SMALL
+          for (int k = 0; k < N; ++k) {
+            double apk = A[p * N + k], aqk = A[q * N + k];
+            A[p * N + k] = c * apk - s * aqk;
+            A[q * N + k] = s * apk + c * aqk;
+          }
+          RM_UNROLL_SMALL
+          for (int k = 0; k < N; ++k) {
+            double vkp = V[k * N + p], vkq = V[k * N + q];
+            V[k * N + p] = c * vkp - s * vkq;
+            V[k * N + q] = s * vkp + c * vkq;
+          }
+        }
+      }
+      continue;
+    }
     for (int p = 0; p < N - 1; ++p) {
       for (int q = p + 1; q < N; ++q) {
         double apq = A[p * N + q];
@@ -181,42 +221,54 @@ RM_HD void upoly_mul(const double* a, int da, const double* b, int db, double* r
 
 // real roots of a degree-`deg` polynomial by sign-change bracketing on [-1, 1] for p(z) and for the reversed
 // polynomial (roots 1/z), then bisection.  Returns the number of roots written (<= max_roots).
+// Two phases per pass so that the 32 hypotheses of a warp stay in lock-step: (1) all 161 sample points are evaluated and
+// the bracketing intervals recorded, (2) a fixed-trip loop bisects the recorded intervals.  With the bisection nested inside
+// the scan (round 1) a warp ran it for the UNION of its lanes' hit intervals - ~100 bisections per pass instead of ~5 -
+// which was most of k_rs_hyp_E's 1.1 ms.
 RM_HDN int upoly_real_roots(const double* p, int deg, double* roots, int max_roots) {
   const int NS = 160;
+  const int MAXB = 10;   // brackets per pass (a degree-10 polynomial has at most 10 real roots)
+  const int NBIS = 60;   // 2 / 160 * 2^-60 is far below the spacing of doubles in [-1, 1]
   int n = 0;
   double rev[16];
   for (int i = 0; i <= deg; ++i) rev[i] = p[deg - i];
   for (int pass = 0; pass < 2 && n < max_roots; ++pass) {
     const double* q = pass == 0 ? p : rev;
+    double blo[MAXB], bhi[MAXB], bflo[MAXB];
+    int nb = 0;
     double a = -1.0, fa = upoly_eval(q, deg, a);
-    for (int i = 1; i <= NS && n < max_roots; ++i) {
+    for (int i = 1; i <= NS; ++i) {
       double b = -1.0 + 2.0 * i / NS, fb = upoly_eval(q, deg, b);
       bool hit = (fa == 0.0) || (fa < 0) != (fb < 0);
       if (fb == 0.0 && i < NS) hit = false;  // will be caught as fa == 0 of the next interval
-      if (hit) {
-        double lo = a, hi = b, flo = fa;
-        if (fa == 0.0) {
-          hi = lo;
-        } else {
-          for (int it = 0; it < 80; ++it) {
-            double mid = 0.5 * (lo + hi), fm = upoly_eval(q, deg, mid);
-            if (fm == 0.0) {
-              lo = hi = mid;
-              break;
-            }
-            if ((fm < 0) == (flo < 0)) lo = mid, flo = fm;
-            else hi = mid;
-          }
-        }
-        double r = 0.5 * (lo + hi);
-        if (pass == 0) {
-          roots[n++] = r;
-        } else if (fabs(r) > 1e-12 && fabs(r) < 1.0) {  // |z| > 1 strictly (|z| == 1 belongs to pass 0)
-          roots[n++] = 1.0 / r;
-        }
+      if (hit && nb < MAXB) {
+        blo[nb] = a, bhi[nb] = (fa == 0.0) ? a : b, bflo[nb] = fa;
+        ++nb;
       }
       a = b;
       fa = fb;
+    }
+    for (int r = 0; r < MAXB; ++r) {  // fixed trip count: lanes without an r-th bracket idle through it
+      if (r >= nb || n >= max_roots) continue;
+      double lo = blo[r], hi = bhi[r], flo = bflo[r];
+      if (lo != hi) {
+        for (int it = 0; it < NBIS; ++it) {
+          double mid = 0.5 * (lo + hi), fm = upoly_eval(q, deg, mid);
+          if (fm == 0.0) {
+            lo = hi = mid;
+          } else if ((fm < 0) == (flo < 0)) {
+            lo = mid, flo = fm;
+          } else {
+            hi = mid;
+          }
+        }
+      }
+      double rt = 0.5 * (lo + hi);
+      if (pass == 0) {
+        roots[n++] = rt;
+      } else if (fabs(rt) > 1e-12 && fabs(rt) < 1.0) {  // |z| > 1 strictly (|z| == 1 belongs to pass 0)
+        roots[n++] = 1.0 / rt;
+      }
     }
   }
   return n;

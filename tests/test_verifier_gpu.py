@@ -111,3 +111,41 @@ def test_argoverse_known_answer(golden_dir):
     # 5 correspondences (:119-136): no crash, failure tuple
     R5, U5, rows5, _ = ver.verify(Keypoints(uv1), Keypoints(uv2), matches[:5], cal, cal)
     assert R5 is None and U5 is None and len(rows5) == 0
+
+
+def test_inlier_iou_and_pose_statistics_over_120_scenes():
+    """north_star lists the inlier mask among the outputs to match; cv2's USAC sampler / local optimisation are not in
+    /root/reference, so the agreement is STATISTICAL: 120 seeded scenes (K in {200, 500, 1000, 2000}, inlier ratio in
+    {0.3, 0.5, 0.8}, 0.5 px noise) through B200Ransac and through cv2 (the oracle), inlier-set IoU and pose error against the
+    ground truth for both.  The distribution is written to gpurun_out/ for profiles/r02_ransac_iou.json."""
+    import json
+    from pathlib import Path
+
+    ver = B200Ransac(True, 4.0)
+    rows_out = []
+    for idx in range(120):
+        k = (200, 500, 1000, 2000)[idx % 4]
+        ratio = (0.3, 0.5, 0.8)[(idx // 4) % 3]
+        kp1, kp2, matches, K, R, t, is_in = vr.synthetic_two_view(1000 + idx, k, ratio)
+        cal = Cal3Bundler(K[0], 0, 0, K[1], K[2])
+        Rm, tm, rows, _ = ver.verify(Keypoints(kp1), Keypoints(kp2), matches, cal, cal)
+        Rc, tc, rows_cv, _, _ = vr.verify_cv2(kp1, kp2, matches, K, K, True, 4.0)
+        assert Rm is not None and Rc is not None
+        mine, cv, gt = set(rows[:, 0].tolist()), set(rows_cv[:, 0].tolist()), set(np.flatnonzero(is_in).tolist())
+        rows_out.append(dict(k=k, ratio=ratio, iou_cv2=len(mine & cv) / max(1, len(mine | cv)), recall_gt=len(mine & gt) / max(1, len(gt)),
+                             recall_gt_cv2=len(cv & gt) / max(1, len(gt)), rot_err=vr.rot_angle_deg(R, Rm.matrix()),
+                             rot_err_cv2=vr.rot_angle_deg(R, Rc), dir_err=vr.dir_angle_deg(t, tm.point3()), dir_err_cv2=vr.dir_angle_deg(t, tc)))
+    iou = np.array([r["iou_cv2"] for r in rows_out])
+    rot, rot_cv = np.array([r["rot_err"] for r in rows_out]), np.array([r["rot_err_cv2"] for r in rows_out])
+    summary = dict(scenes=len(rows_out), iou_min=float(iou.min()), iou_p05=float(np.percentile(iou, 5)), iou_median=float(np.median(iou)),
+                   iou_mean=float(iou.mean()), exact_same_mask=int((iou == 1.0).sum()), rot_err_median=float(np.median(rot)),
+                   rot_err_max=float(rot.max()), rot_err_cv2_median=float(np.median(rot_cv)), rot_err_cv2_max=float(rot_cv.max()),
+                   recall_gt_min=float(min(r["recall_gt"] for r in rows_out)), recall_gt_cv2_min=float(min(r["recall_gt_cv2"] for r in rows_out)))
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "r02_ransac_iou.json").write_text(json.dumps(dict(summary=summary, scenes=rows_out), indent=1))
+    print(summary)
+    # (where the two masks differ most - IoU ~0.9 - it is cv2 that is further from the ground truth: see the per-scene rows)
+    assert summary["iou_median"] > 0.99 and summary["iou_p05"] > 0.95 and summary["iou_min"] > 0.85, summary
+    assert summary["rot_err_max"] <= summary["rot_err_cv2_max"] + 0.1 and summary["rot_err_median"] <= summary["rot_err_cv2_median"] + 0.02, summary
+    assert summary["recall_gt_min"] >= min(0.98, summary["recall_gt_cv2_min"]), summary
