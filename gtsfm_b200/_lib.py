@@ -53,6 +53,7 @@ SIGNATURES = {
     "b2_topk_indices_dev": (_i, [_vp, _vp, _i, _i, _vp, _ip, _vp]),
     "b2_superpoint_detect_host": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _ip, C.POINTER(C.c_uint64)]),
     "b2_superpoint_describe_host": (_i, [_vp, C.c_uint64, _vp, _i, _vp]),
+    "b2_image_resize_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _i, _vp]),
     "b2_lightglue_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_lightglue_match_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip, _vp]),
     "b2_lightglue_match_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(LightGlueParams), _vp, _vp, _ip, _ip]),

@@ -61,6 +61,23 @@ class DeviceFrontEnd:
     def _stream(self):
         return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def ingest(self, image: torch.Tensor, max_resolution: int = 760) -> torch.Tensor:
+        """Loader-side down-size on the device (gtsfm/loader/loader_base.py:160-200 -> gtsfm/utils/images.py:102-129,150-220):
+        uint8 (H, W[, C]) device tensor -> cubic resize so that the short side is `max_resolution` (unchanged if already smaller)."""
+        assert image.dtype == torch.uint8 and image.is_cuda and image.is_contiguous()
+        h, w = int(image.shape[0]), int(image.shape[1])
+        ch = 1 if image.dim() == 2 else int(image.shape[2])
+        if min(h, w) <= max_resolution:
+            return image
+        if h <= w:
+            nh, nw = max_resolution, int(np.round(w * (max_resolution / float(h))).astype(np.int32))
+        else:
+            nh, nw = int(np.round(h * (max_resolution / float(w))).astype(np.int32)), max_resolution
+        out = torch.empty((nh, nw) if image.dim() == 2 else (nh, nw, ch), dtype=torch.uint8, device=self.device)
+        rc = self.lib.b2_image_resize_dev(self.ctx.handle, _lib.ptr(image), h, w, ch, w * ch, _lib.ptr(out), nh, nw, self._stream())
+        self.ctx.check(rc, "image_resize_dev")
+        return out
+
     def detect(self, image: torch.Tensor, mask: Optional[np.ndarray] = None) -> DeviceFeatures:
         """image: uint8 device tensor (H, W) or (H, W, 3|4), contiguous.  One C call (detect -> device top-k -> describe): no
         torch kernels on the path, and the dense map never outlives the call (interleaving images on one handle is safe).

@@ -104,6 +104,14 @@ int b2_superpoint_detect_host(b2_context* ctx, const uint8_t* image, int height,
                               int cap, int* out_n, uint64_t* out_map_token);
 int b2_superpoint_describe_host(b2_context* ctx, uint64_t map_token, const float* xy, int n, float* out_desc);
 
+/* ---- image ingest ------------------------------------------------------------------- */
+/* The loader's cubic resize (gtsfm/utils/images.py:102-129: cv2.resize(INTER_CUBIC) to the size picked by
+ * get_downsampling_factor_per_axis, :150-220) on the device: src / dst are DEVICE uint8 images, `channels` interleaved,
+ * src row pitch in bytes, dst dense.  OpenCV's 11-bit fixed-point arithmetic as restated in oracle/images_ref.py.
+ * Asynchronous on `stream`; feed dst straight into b2_superpoint_detect_dev / b2_superpoint_extract_dev. */
+int b2_image_resize_dev(b2_context* ctx, const uint8_t* src, int height, int width, int channels, size_t pitch, uint8_t* dst,
+                        int new_height, int new_width, void* stream);
+
 /* ---- LightGlue --------------------------------------------------------------------------------------------------- */
 /* `blob`: packed fp32 tensors in the order documented in gtsfm_b200/weights.py::LIGHTGLUE_ORDER (nn.Linear layout
  * (out,in) row-major as in the checkpoint).  n_floats must equal 11851601 (the 251 parameter tensors; the
