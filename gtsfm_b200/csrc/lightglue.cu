@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "linear.cuh"
+#include "assign_ps.cuh"
 
 namespace {
 constexpr int LG_LAYERS = 9;
@@ -64,7 +65,7 @@ struct LightGlueState {
   float thr[LG_LAYERS];
   LgSide side[LG_MAX_SIDES];
   LgPair pair[LG_MAX_PAIRS];
-  DevBuf sim[LG_MAX_PAIRS], counters, attn_part, attn_ml, attn_cnt;
+  DevBuf sim[LG_MAX_PAIRS], counters, attn_part, attn_ml, attn_cnt, as_part, as_bar;
   HostBuf hread;
 };
 
@@ -87,7 +88,7 @@ void lg_destroy(b2_context* ctx) {
     for (DevBuf* b : bufs) b->release();
   }
   for (auto& b : s->sim) b.release();
-  s->attn_part.release(), s->attn_ml.release(), s->attn_cnt.release();
+  s->attn_part.release(), s->attn_ml.release(), s->attn_cnt.release(), s->as_part.release(), s->as_bar.release();
   s->counters.release();
   s->hread.release();
   delete s;
@@ -977,6 +978,20 @@ static int lg_match_batch(b2_context* ctx, b2_lightglue_pair* pairs, int np, con
     const int p = live[li];
     LgSide &a = s->side[2 * p], &b = s->side[2 * p + 1];
     const float* sim = s->sim[p].as<float>();
+    if (assign_ps_fits(1, b.n)) {
+      // persistent cooperative kernel (assign_ps.cuh, KIND 1): row / column log-softmax statistics in one sweep of the
+      // similarity, mutual arg-max in a second one - 2 reads and 1 launch instead of 4 and 4
+      const int G = s->persist_ctas;
+      B2_CUDA(ctx, s->as_part.ensure((size_t)G * 2 * b.n * sizeof(float)));
+      B2_CUDA(ctx, s->as_bar.ensure(16));
+      B2_CUDA(ctx, cudaMemsetAsync(s->as_bar.p, 0, 16, st));
+      SinkArgs sa{};
+      sa.Z = sim, sa.M = a.n, sa.N = b.n, sa.iters = 1, sa.u = a.rmax.as<float>(), sa.v = b.rmax.as<float>();
+      sa.rlog = a.rlog.as<float>(), sa.clog = b.rlog.as<float>(), sa.z0 = a.ls.as<float>(), sa.z1 = b.ls.as<float>();
+      sa.lsg0 = a.lsg.as<float>(), sa.lsg1 = b.lsg.as<float>(), sa.part = s->as_part.as<float>(), sa.bar = s->as_bar.as<unsigned>();
+      sa.best0 = a.amax.as<float>(), sa.arg0 = a.aidx.as<int>(), sa.arg1 = b.aidx.as<int>(), sa.err_flag = s->errflag.as<int>();
+      if ((rc = launch_assign_ps<1>(ctx, st, sa, G, "k_lg_assign"))) return rc;
+    } else {
     B2_LAUNCH(ctx, k_lg_row_stats, cdiv(a.n, 8), 256, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(), a.ls.as<float>(),
               a.lsg.as<float>());
     B2_CHECK_LAUNCH(ctx);
@@ -989,6 +1004,7 @@ static int lg_match_batch(b2_context* ctx, b2_lightglue_pair* pairs, int np, con
     B2_LAUNCH(ctx, k_lg_col_argmax, cdiv(b.n, 32), 1024, 0, st, sim, a.n, b.n, a.rmax.as<float>(), a.rlog.as<float>(),
               b.rmax.as<float>(), b.rlog.as<float>(), a.lsg.as<float>(), b.lsg.as<float>(), b.aidx.as<int>());
     B2_CHECK_LAUNCH(ctx);
+    }
     B2_LAUNCH(ctx, k_lg_filter, 1, 1024, 0, st, a.amax.as<float>(), a.aidx.as<int>(), b.aidx.as<int>(), a.n,
               (float)prm->filter_threshold, a.ind[a.cur].as<int>(), b.ind[b.cur].as<int>(), s->pair[p].out_matches, s->pair[p].out_scores,
               counters + 4 * LG_MAX_PAIRS + p);
