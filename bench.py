@@ -40,6 +40,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 THR_PX = 4.0
+FP16_ATTN = False  # set by --fp16-attention
 MATCH_BATCH = 8  # pairs per lock-step LightGlue batch (the library maximum)
 
 WORKLOADS = {
@@ -76,6 +77,7 @@ def config_of(name: str) -> dict:
         "workload": f"{name}: {w['text']}", "frame": [w["H"], w["W"]], "max_keypoints": w["max_kp"], "lookahead": w["lookahead"],
         "new_frames_per_step": w["new_frames"], "pairs_per_step": pairs, "matcher": w["matcher_text"],
         "match_batch": MATCH_BATCH if w["matcher"] == "lightglue" else 1,
+        "attention": "fp16 single-MMA (reference CUDA numerics, opt-in)" if FP16_ATTN else "split-fp16 x3 (fp32-equivalent, parity-pinned default)",
         "ransac": "5pt, 1000 hypotheses, thr 4 px, conf 0.999999" if w["verify"] else "-", "weights": "seeded synthetic (no checkpoint offline)",
         "l2": "256 MiB flush between timed steps", "parallelism": "pairs sharded per GPU, no data-path collective",
     }
@@ -316,7 +318,7 @@ def run_cuda(args):
     if lg_sd is not None:
         sds.append((lg_sd, weights.LIGHTGLUE_ORDER))
     _broadcast_weights(sds, world, dev)
-    fe = DeviceFrontEnd(sp_sd, lg_sd, device=local, max_keypoints=MAX_KP, superglue_sd=sg_sd)
+    fe = DeviceFrontEnd(sp_sd, lg_sd, device=local, max_keypoints=MAX_KP, superglue_sd=sg_sd, fp16_attention=args.fp16_attention)
     if args.lg_batch:
         fe.ctx.set_option("lightglue_batch", args.lg_batch)
     n_frames = max(LOOKAHEAD, 1) + NEW_FRAMES * (args.warmup + args.steps) * 2 + 4
@@ -597,8 +599,13 @@ def main():
     ap.add_argument("--frames", type=int, default=120, help="--scaling strong: frames of the fixed job (500 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the plugin-path leg (the line is then not a valid bench line)")
+    ap.add_argument("--fp16-attention", action="store_true",
+                    help="opt-in mode: the reference's CUDA numerics for attention (fp16 flash SDPA, one MMA per product); NOT the "
+                         "parity-pinned default - the line says so in config.matcher")
     ap.add_argument("--lg-batch", type=int, default=0, help="experiments: pairs per lock-step LightGlue batch inside the library (0 = default)")
     args = ap.parse_args()
+    global FP16_ATTN
+    FP16_ATTN = bool(args.fp16_attention)
     if args.impl == "reference":
         run_reference(args)
     elif args.scaling == "strong":

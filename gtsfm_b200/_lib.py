@@ -18,7 +18,7 @@ class B200Error(RuntimeError):
 
 class LightGlueParams(C.Structure):
     _fields_ = [("depth_confidence", C.c_double), ("width_confidence", C.c_double), ("filter_threshold", C.c_double),
-                ("prune_min_kpts", C.c_int)]
+                ("prune_min_kpts", C.c_int), ("fp16_attention", C.c_int)]
 
 
 class LightGluePair(C.Structure):

@@ -102,6 +102,10 @@ __device__ __forceinline__ AttnPsSeg attn_ps_decode(const AttnPsArgs& a, int w, 
   return s;
 }
 
+// SINGLE = the reference's CUDA numerics (lightglue.py:116-121: q, k, v cast to half, fp16 flash SDPA, result cast back):
+// only the hi planes take part - ONE tcgen05.mma per product instead of three - and the output is rounded to fp16.  Opt-in
+// (b2_lightglue_params.fp16_attention); the default exact path reproduces the fp32 CPU front-end.
+template <bool SINGLE>
 static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_constant__ AttnPsMaps maps, const __grid_constant__ AttnPsArgs args) {
   extern __shared__ unsigned char ap_raw[];
   const uint32_t raw = tc::smem_u32(ap_raw);
@@ -145,17 +149,18 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           const int g = ge + e, s = g % AS_NS;
           if (g >= AS_NS) ok = tc::mbar_wait(&kv_empty[s], ((g / AS_NS) - 1) & 1) && ok;
           const bool hk = e < sg.T, hv = e >= 2;
-          tc::mbar_expect_tx(&kv_full[s], (hk ? AS_HALF : 0) + (hv ? AS_HALF : 0));
+          constexpr int PART = SINGLE ? AW_KV_BYTES : AS_HALF;  // bytes of one operand tile that are really fetched
+          tc::mbar_expect_tx(&kv_full[s], (hk ? PART : 0) + (hv ? PART : 0));
           const uint32_t dst = smem0 + s * AS_STAGE;
           if (hk) {
             const int row = sg.h * Nk + (sg.tile0 + e) * AW_KV;
             tc::tma_load_2d(dst, &maps.kh[sg.z], &kv_full[s], 0, row);
-            tc::tma_load_2d(dst + AW_KV_BYTES, &maps.kl[sg.z], &kv_full[s], 0, row);
+            if (!SINGLE) tc::tma_load_2d(dst + AW_KV_BYTES, &maps.kl[sg.z], &kv_full[s], 0, row);
           }
           if (hv) {
             const int row = sg.h * Nk + (sg.tile0 + e - 2) * AW_KV;
             tc::tma_load_2d(dst + AS_HALF, &maps.vh[sg.z], &kv_full[s], 0, row);
-            tc::tma_load_2d(dst + AS_HALF + AW_KV_BYTES, &maps.vl[sg.z], &kv_full[s], 0, row);
+            if (!SINGLE) tc::tma_load_2d(dst + AS_HALF + AW_KV_BYTES, &maps.vl[sg.z], &kv_full[s], 0, row);
           }
         }
         ge += sg.T + 2;
@@ -183,8 +188,10 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           const uint64_t adv = (uint64_t)(ks * 2);
           const uint32_t ac = (uint32_t)(ks * 8);
           tc::umma_f16_ts_w(tS, tQh + ac, dKh + adv, idS, ks ? 1u : 0u);
-          tc::umma_f16_ts_w(tS, tQh + ac, dKl + adv, idS, 1u);
-          tc::umma_f16_ts_w(tS, tQl + ac, dKh + adv, idS, 1u);
+          if (!SINGLE) {
+            tc::umma_f16_ts_w(tS, tQh + ac, dKl + adv, idS, 1u);
+            tc::umma_f16_ts_w(tS, tQl + ac, dKh + adv, idS, 1u);
+          }
         }
         tc::umma_commit_w(&s_full[q * 2 + buf]);
       };
@@ -198,8 +205,10 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           const uint32_t ac = (uint32_t)(ks * 8);
           const uint64_t advV = (uint64_t)(ks * 128);
           tc::umma_f16_ts_w(tO, tPh + ac, dVh + advV, idO, (j | ks) ? 1u : 0u);
-          tc::umma_f16_ts_w(tO, tPh + ac, dVl + advV, idO, 1u);
-          tc::umma_f16_ts_w(tO, tPl + ac, dVh + advV, idO, 1u);
+          if (!SINGLE) {
+            tc::umma_f16_ts_w(tO, tPh + ac, dVl + advV, idO, 1u);
+            tc::umma_f16_ts_w(tO, tPl + ac, dVh + advV, idO, 1u);
+          }
         }
         tc::umma_commit_w(&o_full[q]);
       };
@@ -247,7 +256,7 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
       const int qrow = sg.q0 + q * AW_Q + r;
       uint32_t wv[32];
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
+      for (int pl = 0; pl < (SINGLE ? 1 : 2); ++pl) {
         const __half* src = (pl ? pr.Ql : pr.Qh) + ((size_t)sg.h * pr.Nq + qrow) * 64;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -315,15 +324,17 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           const float2 p2 = make_float2(tc::ex2(e.x), tc::ex2(e.y));
           rs2 = tc::fadd2(rs2, p2);
           const __half2 hh = __floats2half2_rn(p2.x, p2.y);
-          const float2 d = tc::ffma2(__half22float2(hh), neg1, p2);  // p - hi, exact
-          const __half2 ll = __floats2half2_rn(d.x, d.y);
           ph[jj] = *reinterpret_cast<const uint32_t*>(&hh);
-          pl[jj] = *reinterpret_cast<const uint32_t*>(&ll);
+          if (!SINGLE) {
+            const float2 d = tc::ffma2(__half22float2(hh), neg1, p2);  // p - hi, exact
+            const __half2 ll = __floats2half2_rn(d.x, d.y);
+            pl[jj] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
         }
         l_i += rs2.x + rs2.y;
         h_s = (i + 1 < T) && tc::mbar_test(&s_full[q * 2 + ((gi + 1) & 1)], ((gi + 1) >> 1) & 1);
         tc::tmem_st32(tS, ph);  // P_i over S_i (this thread's own row; every column of it is already in registers)
-        tc::tmem_st32(tS + 32, pl);
+        if (!SINGLE) tc::tmem_st32(tS + 32, pl);
         tc::tmem_st_wait();
         if (!waited) ok = tc::mbar_wait(&o_full[q], (gi - 1) & 1) && ok;  // every phase is observed once
         tc::fence_before_sync();
@@ -349,7 +360,14 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           for (int c = 0; c < 8; ++c) {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) {
+              if (SINGLE) {  // SDPA returns half: the message is the fp16 rounding of the fp32 accumulator
+                const __half2 hh = __floats2half2_rn(tc::clamp_h(o[8 * c + 2 * i] * inv), tc::clamp_h(o[8 * c + 2 * i + 1] * inv));
+                hi[i] = *reinterpret_cast<const uint32_t*>(&hh), lo[i] = 0u;
+              } else {
+                tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+              }
+            }
             dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
@@ -401,7 +419,14 @@ static __global__ void __launch_bounds__(AS_THREADS, 1) k_flash_ps(const __grid_
           for (int c = 0; c < 8; ++c) {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) {
+              if (SINGLE) {  // SDPA returns half: the message is the fp16 rounding of the fp32 accumulator
+                const __half2 hh = __floats2half2_rn(tc::clamp_h(o[8 * c + 2 * i] * inv), tc::clamp_h(o[8 * c + 2 * i + 1] * inv));
+                hi[i] = *reinterpret_cast<const uint32_t*>(&hh), lo[i] = 0u;
+              } else {
+                tc::split2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv, hi[i], lo[i]);
+              }
+            }
             dh[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             dl[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }

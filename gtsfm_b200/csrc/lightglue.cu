@@ -656,7 +656,8 @@ extern "C" int b2_lightglue_set_weights(b2_context* ctx, const float* blob, size
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaDeviceSynchronize());
   B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_ps<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AS_SMEM));
   s->use_tc = !b2_force_simt(ctx);
   B2_CUDA(ctx, cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
   B2_CUDA(ctx, s->hread.ensure(8 * LG_MAX_PAIRS * sizeof(int)));
@@ -756,7 +757,7 @@ static int lg_out_and_ffn(b2_context* ctx, cudaStream_t st, LightGlueState* s, c
   return run_linear(ctx, st, tw, f3, act.n);
 }
 
-static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer) {
+static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer, bool fp16_attn) {
   const SelfW& w = s->sw[layer];
   const TcWeights tw = lg_tw(s);
   int rc;
@@ -788,11 +789,11 @@ static int lg_self_layer(b2_context* ctx, cudaStream_t st, LightGlueState* s, co
     LgSide& a = s->side[act.side[i]];
     fj[i] = {&a.q, &a.k, &a.v, &a.ctx, a.n, a.n, a.cap, a.cap};
   }
-  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f))) return rc;
+  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f, fp16_attn))) return rc;
   return lg_out_and_ffn(ctx, st, s, act, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
-static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer) {
+static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, const LgActive& act, int layer, bool fp16_attn) {
   const CrossW& w = s->cw[layer];
   const TcWeights tw = lg_tw(s);
   int rc;
@@ -817,7 +818,7 @@ static int lg_cross_block(b2_context* ctx, cudaStream_t st, LightGlueState* s, c
     LgSide &a = s->side[act.side[i]], &b = s->side[act.side[i] ^ 1];
     fj[i] = {&a.q, &b.q, &b.v, &a.ctx, a.n, b.n, a.cap, b.cap};
   }
-  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f))) return rc;
+  if ((rc = run_flash(ctx, st, tw, fj, act.n, 0.125f, fp16_attn))) return rc;
   return lg_out_and_ffn(ctx, st, s, act, w.wout, w.bout, w.w0, w.b0, w.lng, w.lnb, w.w3, w.b3);
 }
 
@@ -865,8 +866,9 @@ static int lg_match_batch(b2_context* ctx, b2_lightglue_pair* pairs, int np, con
   int* counters = s->counters.as<int>();
   int* hread = s->hread.as<int>();
   for (int layer = 0; layer < LG_LAYERS && act.n > 0; ++layer) {
-    if ((rc = lg_self_layer(ctx, st, s, act, layer))) return rc;
-    if ((rc = lg_cross_block(ctx, st, s, act, layer))) return rc;
+    const bool fp16_attn = prm->fp16_attention != 0 && s->use_tc;
+    if ((rc = lg_self_layer(ctx, st, s, act, layer, fp16_attn))) return rc;
+    if ((rc = lg_cross_block(ctx, st, s, act, layer, fp16_attn))) return rc;
     for (int p = 0; p < np; ++p)
       if (s->pair[p].active) s->pair[p].stop = layer;
     if (layer == LG_LAYERS - 1) break;

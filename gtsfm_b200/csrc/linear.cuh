@@ -129,7 +129,7 @@ struct FlashJob {
   int nq, nk;
   int capq, capk;  // allocated rows of the query-side / key-side buffers (lo plane offset = cap * 256 halves)
 };
-static int run_flash(b2_context* ctx, cudaStream_t st, const TcWeights& tw, const FlashJob* jobs, int np, float scale) {
+static int run_flash(b2_context* ctx, cudaStream_t st, const TcWeights& tw, const FlashJob* jobs, int np, float scale, bool fp16_single = false) {
   if (np <= 0) return B2_OK;
   if (np > AP_MAXP) return b2_fail(ctx, B2_ERR_ARG, "run_flash: too many problems in one launch");
   if (!tw.use_tc) {
@@ -185,7 +185,8 @@ static int run_flash(b2_context* ctx, cudaStream_t st, const TcWeights& tw, cons
   pa.Opart = tw.attn_part->as<float>(), pa.ml = tw.attn_ml->as<float>();
   pa.scale = scale, pa.err_flag = tw.err;
   b2_prof_work(ctx, "k_flash_ps", work);
-  B2_LAUNCH(ctx, k_flash_ps, ncta, AS_THREADS, AS_SMEM, st, tmaps, pa);
+  if (fp16_single) B2_LAUNCH(ctx, k_flash_ps<true>, ncta, AS_THREADS, AS_SMEM, st, tmaps, pa);
+  else B2_LAUNCH(ctx, k_flash_ps<false>, ncta, AS_THREADS, AS_SMEM, st, tmaps, pa);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
 }

@@ -30,7 +30,7 @@ class LightGlueEngine:
         self.d2h_bytes = 0
 
     def match(self, kp0, desc0, kp1, desc1, depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1,
-              prune_min_kpts=-1, return_scores=False):
+              prune_min_kpts=-1, return_scores=False, fp16_attention=False):
         kp0 = np.ascontiguousarray(kp0, np.float32)
         kp1 = np.ascontiguousarray(kp1, np.float32)
         desc0 = np.ascontiguousarray(desc0, np.float32)
@@ -40,7 +40,7 @@ class LightGlueEngine:
         out = np.empty((cap, 2), np.int64)
         sc = np.empty(cap, np.float32)
         k, stop = _lib.C.c_int(0), _lib.C.c_int(0)
-        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, prune_min_kpts)
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, prune_min_kpts, 1 if fp16_attention else 0)
         sent0 = self.ctx.h2d_bytes()
         rc = self.ctx.lib.b2_lightglue_match_host(self.ctx.handle, _lib.ptr(kp0), _lib.ptr(desc0), n0, _lib.ptr(kp1),
                                                   _lib.ptr(desc1), n1, _lib.C.byref(prm), _lib.ptr(out), _lib.ptr(sc),
@@ -68,7 +68,7 @@ class B200LightGlueMatcher(MatcherBase):
     """
 
     def __init__(self, features: str = "superpoint", use_cuda: bool = True, weights_path: Union[Path, str, dict, None] = None,
-                 device: int = 0, cpu_semantics: bool = True, feature_cache: bool = False):
+                 device: int = 0, cpu_semantics: bool = True, feature_cache: bool = False, fp16_attention: bool = False):
         super().__init__()
         if features != "superpoint":
             raise ValueError(f"Unsupported features: {features} (this build serves the SuperPoint LightGlue only)")
@@ -82,6 +82,7 @@ class B200LightGlueMatcher(MatcherBase):
         self._device = device
         self._cpu_semantics = cpu_semantics
         self._feature_cache = bool(feature_cache)
+        self._fp16_attention = bool(fp16_attention)  # opt-in: the reference's CUDA numerics (fp16 flash SDPA), ~2x faster attention
         self._engine: Optional[LightGlueEngine] = None
 
     def __getstate__(self):
@@ -104,7 +105,7 @@ class B200LightGlueMatcher(MatcherBase):
             raise AssertionError("LightGlue(superpoint) expects 256-dimensional descriptors")  # lightglue.py:509-510
         eng = self._ensure_engine()
         return eng.match(keypoints_i1.coordinates, descriptors_i1, keypoints_i2.coordinates, descriptors_i2,
-                         prune_min_kpts=-1 if self._cpu_semantics else 1536)
+                         prune_min_kpts=-1 if self._cpu_semantics else 1536, fp16_attention=self._fp16_attention)
 
 
 SUPERGLUE_DESC_DIM = 256

@@ -36,7 +36,7 @@ RESERVE_SMS_FOR_VERIFY = int(os.environ.get("B2_RESERVE_SMS", "8"))  # k_rs_hyp_
 
 class DeviceFrontEnd:
     def __init__(self, superpoint_sd, lightglue_sd=None, device: int = 0, max_keypoints: int = 5000, cpu_semantics: bool = True,
-                 ctx: Optional[_lib.Context] = None, superglue_sd=None):
+                 ctx: Optional[_lib.Context] = None, superglue_sd=None, fp16_attention: bool = False):
         if not torch.cuda.is_available():
             raise _lib.B200Error("DeviceFrontEnd needs a CUDA device; there is no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -44,6 +44,7 @@ class DeviceFrontEnd:
         self.lib = self.ctx.lib
         self.max_keypoints = max_keypoints
         self.prune_min = -1 if cpu_semantics else 1536
+        self.fp16_attention = 1 if fp16_attention else 0  # opt-in: the reference's CUDA numerics (lightglue.py:116-121)
         blob = weights.pack_superpoint(weights.load_state_dict(superpoint_sd))
         self.ctx.check(self.lib.b2_superpoint_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superpoint_set_weights")
         if lightglue_sd is not None:
@@ -125,7 +126,7 @@ class DeviceFrontEnd:
         cap = max(1, min(len(a), len(b)))
         out = torch.empty((cap, 2), dtype=torch.int64, device=self.device)
         k, stop = _lib.C.c_int(0), _lib.C.c_int(0)
-        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min)
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min, self.fp16_attention)
         rc = self.lib.b2_lightglue_match_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(a.desc), len(a), _lib.ptr(b.kp), _lib.ptr(b.desc),
                                              len(b), _lib.C.byref(prm), _lib.ptr(out), None, _lib.C.byref(k), _lib.C.byref(stop),
                                              self._stream())
@@ -158,7 +159,7 @@ class DeviceFrontEnd:
             arr[i].kp0, arr[i].desc0, arr[i].n0 = a.kp.data_ptr(), a.desc.data_ptr(), len(a)
             arr[i].kp1, arr[i].desc1, arr[i].n1 = b.kp.data_ptr(), b.desc.data_ptr(), len(b)
             arr[i].out_matches, arr[i].out_scores = out.data_ptr(), None
-        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min)
+        prm = _lib.LightGlueParams(depth_confidence, width_confidence, filter_threshold, self.prune_min, self.fp16_attention)
         rc = self.lib.b2_lightglue_match_batched_dev(self.ctx.handle, arr, n, _lib.C.byref(prm), self._stream())
         self.ctx.check(rc, "lightglue_match_batched_dev")
         return [(outs[i][: arr[i].out_k], int(arr[i].out_stop_layer)) for i in range(n)]

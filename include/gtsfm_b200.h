@@ -125,6 +125,10 @@ typedef struct b2_lightglue_params {
   double width_confidence; /* 0.99; <= 0 disables pruning      (lightglue.py:331)            */
   double filter_threshold; /* 0.1                              (lightglue.py:332)            */
   int prune_min_kpts;      /* -1 = reference CPU semantics (prune at every layer); 1536 = its CUDA+flash value */
+  int fp16_attention;      /* 0 (default): fp32-equivalent attention, what the reference's CPU front-end computes and the fixtures
+                            * pin.  1: the reference's CUDA numerics (lightglue.py:116-121: q, k, v cast to half, fp16 flash SDPA,
+                            * half result cast back) - one tensor-core product instead of three; descriptors then agree with the
+                            * fp32 path to ~1e-3 and match indices are no longer guaranteed bit-identical to the CPU reference. */
 } b2_lightglue_params;
 
 /* kp: [n][2] float (x, y) pixels; desc: [n][256] float.  out_matches: [min(n0,n1)][2] int64 rows (idx0, idx1)

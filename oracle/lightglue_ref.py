@@ -62,18 +62,29 @@ def _ffn(sd, p, x, msg):
     return x + _lin(sd, p + "ffn.3", F.gelu(h))
 
 
-def self_block(sd, i, x, cs):
+def _half_sdpa(q, k, v):
+    """What the reference's CUDA branch computes (lightglue.py:116-121): q, k, v cast to half, flash SDPA (fp32 accumulation
+    of half operands), half result cast back.  Emulated on the CPU: operands and result rounded to fp16, arithmetic in fp32."""
+    q, k, v = (t.half().float() for t in (q, k, v))
+    att = F.softmax(q @ k.transpose(-1, -2) * (q.shape[-1] ** -0.5), -1)
+    return (att @ v).half().float()
+
+
+def self_block(sd, i, x, cs, fp16_attention=False):
     """lightglue.py:140-172."""
     p = f"transformers.{i}.self_attn."
     qkv = _lin(sd, p + "Wqkv", x).unflatten(-1, (HEADS, -1, 3)).transpose(0, 1)  # (H, N, 64, 3)
     q, k, v = _rot(qkv[..., 0], cs), _rot(qkv[..., 1], cs), qkv[..., 2]
-    att = F.softmax(q @ k.transpose(-1, -2) * (q.shape[-1] ** -0.5), -1)
-    ctx = (att @ v).transpose(0, 1).flatten(-2)
+    if fp16_attention:
+        ctx = _half_sdpa(q, k, v).transpose(0, 1).flatten(-2)
+    else:
+        att = F.softmax(q @ k.transpose(-1, -2) * (q.shape[-1] ** -0.5), -1)
+        ctx = (att @ v).transpose(0, 1).flatten(-2)
     return _ffn(sd, p, x, _lin(sd, p + "out_proj", ctx))
 
 
-def cross_block(sd, i, x0, x1):
-    """lightglue.py:175-230, CPU branch :216-223."""
+def cross_block(sd, i, x0, x1, fp16_attention=False):
+    """lightglue.py:175-230, CPU branch :216-223 (fp16_attention: the CUDA + flash branch :210-214)."""
     p = f"transformers.{i}.cross_attn."
 
     def heads(t):
@@ -81,10 +92,13 @@ def cross_block(sd, i, x0, x1):
 
     qk0, qk1 = heads(_lin(sd, p + "to_qk", x0)), heads(_lin(sd, p + "to_qk", x1))
     v0, v1 = heads(_lin(sd, p + "to_v", x0)), heads(_lin(sd, p + "to_v", x1))
-    s = (qk0.shape[-1] ** -0.5) ** 0.5
-    sim = (qk0 * s) @ (qk1 * s).transpose(-1, -2)
-    m0 = F.softmax(sim, -1) @ v1
-    m1 = F.softmax(sim.transpose(-1, -2), -1) @ v0
+    if fp16_attention:
+        m0, m1 = _half_sdpa(qk0, qk1, v1), _half_sdpa(qk1, qk0, v0)
+    else:
+        s = (qk0.shape[-1] ** -0.5) ** 0.5
+        sim = (qk0 * s) @ (qk1 * s).transpose(-1, -2)
+        m0 = F.softmax(sim, -1) @ v1
+        m1 = F.softmax(sim.transpose(-1, -2), -1) @ v0
     m0 = _lin(sd, p + "to_out", m0.transpose(0, 1).flatten(-2))
     m1 = _lin(sd, p + "to_out", m1.transpose(0, 1).flatten(-2))
     return _ffn(sd, p, x0, m0), _ffn(sd, p, x1, m1)
@@ -107,7 +121,7 @@ def log_assignment(sd, i, d0, d1):
 
 def lightglue_match(
     kp0: np.ndarray, desc0: np.ndarray, kp1: np.ndarray, desc1: np.ndarray, sd: Dict[str, np.ndarray],
-    trace: Optional[dict] = None,
+    trace: Optional[dict] = None, fp16_attention: bool = False,
 ) -> np.ndarray:
     """-> (K, 2) int64 rows (index into set 0, index into set 1), ascending in column 0 (lightglue.py:594-602)."""
     m, n = len(kp0), len(kp1)
@@ -127,9 +141,9 @@ def lightglue_match(
             if d0.shape[0] == 0 or d1.shape[0] == 0:
                 break
             sizes.append((d0.shape[0], d1.shape[0]))
-            d0 = self_block(sd, i, d0, cs0)
-            d1 = self_block(sd, i, d1, cs1)
-            d0, d1 = cross_block(sd, i, d0, d1)
+            d0 = self_block(sd, i, d0, cs0, fp16_attention)
+            d1 = self_block(sd, i, d1, cs1, fp16_attention)
+            d0, d1 = cross_block(sd, i, d0, d1, fp16_attention)
             if trace is not None:
                 trace[f"desc0_l{i}"] = d0.numpy().copy()
                 trace[f"desc1_l{i}"] = d1.numpy().copy()
