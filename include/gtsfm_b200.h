@@ -182,7 +182,10 @@ typedef struct b2_ransac_params {
   double threshold;   /* inlier threshold: max point-to-epipolar-line style distance (same unit as the points):      */
                       /* thr_px / fx for E on normalised points, thr_px for F on pixels (ransac.py:79,107)           */
   double confidence;  /* 0.999999 (ransac.py:22)                                                                     */
-  int max_iters;      /* hypothesis budget: E 1000 (cv2 default, ransac.py:74-81) ; F capped by the library at 4096  */
+  int max_iters;      /* hypothesis budget (cv2 maxIters): E 1000 (cv2 default, ransac.py:74-81), clamped to 65 536; F: the       */
+                      /* reference passes 10^6, the library clamps to 262 144 and stops earlier through the standard        */
+                      /* confidence bound.  E only: when the bound says max_iters (<= 4096) samples were NOT enough for      */
+                      /* `confidence`, up to 4 x max_iters further samples are drawn (decided on the device).                */
   uint64_t seed;      /* fixed per call => run-to-run identical results (repro test)           */
 } b2_ransac_params;
 
