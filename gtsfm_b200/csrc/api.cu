@@ -33,6 +33,7 @@ extern "C" void b2_destroy(b2_context* ctx) {
   lg_destroy(ctx);
   sg_destroy(ctx);
   rs_destroy(ctx);
+  rt_destroy(ctx);
   for (auto& b : ctx->stage_d) b.release();
   for (auto& b : ctx->stage_h) b.release();
   for (auto& e : ctx->fcache) e.buf.release();

@@ -82,6 +82,7 @@ struct SuperPointState;
 struct LightGlueState;
 struct SuperGlueState;
 struct RansacState;
+struct RetrievalState;
 
 // Device copies of host feature arrays handed to the *_host matcher entry points.  GTSfM matches one image's (keypoints,
 // descriptors) against ~20-40 partners, always passing the same host arrays, so re-uploading 5 MB per image per pair is
@@ -113,6 +114,7 @@ struct b2_context {
   LightGlueState* lg = nullptr;
   SuperGlueState* sg = nullptr;
   RansacState* rs = nullptr;
+  RetrievalState* rt = nullptr;
   // staging shared by the *_host entry points
   DevBuf stage_d[8];
   HostBuf stage_h[4];
@@ -174,6 +176,7 @@ void sp_destroy(b2_context* ctx);
 void lg_destroy(b2_context* ctx);
 void sg_destroy(b2_context* ctx);
 void rs_destroy(b2_context* ctx);
+void rt_destroy(b2_context* ctx);
 
 // shared device helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

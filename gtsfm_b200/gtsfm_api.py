@@ -26,6 +26,10 @@ try:  # pragma: no cover - exercised only inside a full GTSfM environment
     from gtsfm.frontend.matcher.matcher_base import MatcherBase
     from gtsfm.frontend.verifier.verifier_base import VerifierBase
 
+    try:  # the retriever base drags in gtsfm.evaluation.metrics -> h5py / open3d: optional on its own
+        from gtsfm.retriever.retriever_base import RetrieverBase
+    except Exception:  # noqa: BLE001
+        RetrieverBase = None
     HAVE_GTSFM = True
 except Exception:  # noqa: BLE001 - any import problem (gtsam, dask, hydra ...) means "not a GTSfM environment"
     HAVE_GTSFM = False
@@ -104,6 +108,8 @@ except Exception:  # noqa: BLE001 - any import problem (gtsam, dask, hydra ...) 
         @abc.abstractmethod
         def match(self, keypoints_i1, keypoints_i2, descriptors_i1, descriptors_i2, im_shape_i1, im_shape_i2) -> np.ndarray:
             ...
+
+    RetrieverBase = None
 
     NUM_MATCHES_REQ_E_MATRIX = 5
     NUM_MATCHES_REQ_F_MATRIX = 8
@@ -184,3 +190,20 @@ except Exception:  # noqa: BLE001
                 g = 1 + self._k1 * r2 + self._k2 * r2 * r2
                 xu, yu = x / g, y / g
             return np.array([xu, yu])
+
+
+if RetrieverBase is None:
+
+    class RetrieverBase(abc.ABC):  # mirrors gtsfm/retriever/retriever_base.py:17-60
+        def set_max_frame_lookahead(self, n) -> None:
+            raise AttributeError(f"{type(self).__name__} has no max_frame_lookahead")
+
+        def set_num_matched(self, n) -> None:
+            raise AttributeError(f"{type(self).__name__} has no num_matched")
+
+        @abc.abstractmethod
+        def get_image_pairs(self, global_descriptors, image_fnames, plots_output_dir=None):
+            ...
+
+        def save_diagnostics(self, image_fnames, pairs, plots_output_dir) -> None:
+            return None

@@ -209,6 +209,14 @@ int b2_ransac_essential_dev(b2_context* ctx, const float* kp1, const float* kp2,
 int b2_recover_pose_host(b2_context* ctx, const double* E, const double* x1, const double* x2, int k, double* out_R,
                          double* out_t, int* out_num_good);
 
+/* ---- retrieval front ---------------------------------------------------------------- */
+/* gtsfm/retriever/similarity_retriever.py:86-260: sim = G G^T of the global image descriptors (desc: HOST [n][dim] fp32,
+ * dim a multiple of 64), then per query image i its `num_matched` best partners among j > i with sim >= min_score, best
+ * first.  out_partners: HOST [n][min(num_matched, n)] int32, -1 = no (further) partner; out_sim: HOST [n][n] or NULL.
+ * (The descriptor network itself - NetVLAD / MegaLoc - is not part of this library.) */
+int b2_similarity_pairs_host(b2_context* ctx, const float* desc, int n, int dim, int num_matched, float min_score,
+                             int32_t* out_partners, float* out_sim);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,6 +320,50 @@ def golden_lund_door():
     print(f"lund door: 66 pairs, matches per pair min/median/max {min(n_matches)}/{int(np.median(n_matches))}/{max(n_matches)}")
 
 
+def retriever_descriptors(n=130, dim=512, seed=7):
+    """A walk through descriptor space: neighbours in the sequence are similar (like NetVLAD over a video), unit norm."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal(dim)
+    out = []
+    for _ in range(n):
+        base = base + 0.35 * rng.standard_normal(dim)
+        v = base + 0.1 * rng.standard_normal(dim)
+        out.append((v / np.linalg.norm(v)).astype(np.float32))
+    return np.stack(out)
+
+
+def golden_retriever():
+    """The reference's SimilarityRetriever (gtsfm/retriever/similarity_retriever.py) on seeded descriptors; matplotlib, dask
+    and gtsam are not installed, and gtsfm.evaluation.metrics (type names in retriever_base.py only) pulls in h5py / open3d,
+    so those are replaced by empty stand-ins: the retriever module and its base are the reference's own code."""
+    import types
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, n):
+            if n.startswith("__"):
+                raise AttributeError(n)
+            return type(n, (), {"__init__": lambda self, *a, **k: None})
+
+    for name in ("gtsam", "gtsam.noiseModel", "dask", "dask.distributed", "distributed", "matplotlib", "matplotlib.pyplot", "gtsfm.evaluation.metrics"):
+        sys.modules.setdefault(name, _Stub(name))
+    sys.path.insert(0, "/root/reference")
+    from gtsfm.retriever.similarity_retriever import SimilarityRetriever
+
+    g = retriever_descriptors()
+    out = {"descriptors": g}
+    cases = [(5, 0.1), (200, 0.3), (2, -1.0), (10, 0.55)]
+    for c, (k, ms) in enumerate(cases):
+        r = SimilarityRetriever(num_matched=k, min_score=ms)
+        pairs = r.get_image_pairs([d for d in g], [f"{i}.jpg" for i in range(len(g))])
+        out[f"pairs_{c}"] = np.asarray(pairs, np.int32).reshape(-1, 2)
+        out[f"case_{c}"] = np.asarray([k, ms], np.float64)
+        if c == 0:
+            out["sim"] = r._latest_similarity_matrix.numpy()
+        print("retriever case", c, k, ms, len(pairs))
+    out["versions"] = versions()
+    np.savez_compressed(OUT / "retriever.npz", **out)
+
+
 def main():
     assert ref_modules.available(), "/root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -337,6 +381,7 @@ def main():
     golden_superpoint_mp1()
     golden_superglue_large()
     golden_lund_door()
+    golden_retriever()
 
 
 if __name__ == "__main__":
