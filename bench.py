@@ -58,7 +58,7 @@ WORKLOADS = {
         text="SuperPoint+SuperGlue+RANSAC-5pt two-view, synthetic 640x480 sequence, Sequential lookahead 20 (BASELINE configs[3] verbatim)",
         matcher_text="SuperGlue 18 layers, 20 Sinkhorn iterations, threshold 0.2 (synthetic 'sharp' weights)"),
     "superpoint_only": dict(
-        H=480, W=640, max_kp=5000, matcher=None, profile=None, lookahead=0, new_frames=32, verify=False, dominant="k_conv_tma",
+        H=480, W=640, max_kp=5000, matcher=None, profile=None, lookahead=0, new_frames=32, verify=False, dominant="k_conv_ps",
         text="SuperPoint detect+describe only, synthetic 640x480 frames (BASELINE configs[1])", matcher_text="-"),
     "small_stop": dict(
         H=480, W=640, max_kp=1024, matcher="lightglue", profile="stop", lookahead=20, new_frames=2, verify=True, dominant="k_flash",
@@ -411,7 +411,7 @@ def run_cuda(args):
             family_ms["k_rs_ (verification stream, overlapped)"] = {"ms_per_step": ms, "launches": n}
     # detect-only rate (BASELINE configs[1] shape) and the encoder convolutions' rate
     torch.cuda.synchronize()
-    fe.ctx.profile_start("k_conv_tma")
+    fe.ctx.profile_start("k_conv_ps")
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d0.record()
     for j in range(16):

@@ -12,7 +12,8 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "conv_tma.cuh"
+#include "conv_ps.cuh"
+#include "linear.cuh"
 
 namespace {
 
@@ -31,7 +32,12 @@ struct SuperPointState {
   float* w[SP_NCONV] = {};
   float* b[SP_NCONV] = {};
   // tcgen05 path: 3x3 weights as [cout][tap * cin] split-fp16 planes (B operand of the implicit GEMM)
-  DevBuf wsplit_h, wsplit_l, errflag;
+  DevBuf wsplit_h, wsplit_l, errflag, conv_dbg, logits;
+  struct ConvMapCache {
+    ConvPsMaps maps;
+    const void *ih = nullptr, *wh = nullptr;
+    int H = 0, W = 0;
+  } conv_maps[12];
   size_t wsoff[SP_NCONV] = {};
   bool use_tc = true;
   // workspace
@@ -46,7 +52,7 @@ struct SuperPointState {
 void sp_destroy(b2_context* ctx) {
   if (!ctx->sp) return;
   SuperPointState* s = ctx->sp;
-  DevBuf* bufs[] = {&s->wblob, &s->wsplit_h, &s->wsplit_l, &s->errflag, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
+  DevBuf* bufs[] = {&s->wblob, &s->wsplit_h, &s->wsplit_l, &s->errflag, &s->conv_dbg, &s->logits, &s->gray, &s->a0, &s->a1, &s->feat, &s->head, &s->heat, &s->nms,
                     &s->rowcnt, &s->rowoff, &s->dense, &s->kpxy, &s->kpsc, &s->sel_idx, &s->sel_cnt};
   for (DevBuf* b : bufs) b->release();
   delete s;
@@ -75,41 +81,63 @@ __global__ void k_to_gray(const uint8_t* __restrict__ img, size_t pitch, int cha
 }
 
 // conv1a: 1 -> 64 channels, 3x3, pad 1, bias, ReLU; input gray u8 / 255 (gtsfm/.../superpoint.py:74).
-// block = 256 threads = 16 pixels x 16 channel groups of 4.
-__global__ void __launch_bounds__(256) k_conv1a(const uint8_t* __restrict__ gray, const float* __restrict__ wt /*[9][64]*/,
-                                                 const float* __restrict__ bias, float* __restrict__ out, int H, int W,
-                                                 __half* __restrict__ oh, __half* __restrict__ ol) {
-  __shared__ float ws[9 * 64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 9 * 64; i += 256) ws[i] = wt[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  long long pix = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
-  int cg = threadIdx.x & 15;
-  if (pix >= (long long)H * W) return;
-  int y = (int)(pix / W), x = (int)(pix % W);
-  float acc[4] = {bs[cg * 4 + 0], bs[cg * 4 + 1], bs[cg * 4 + 2], bs[cg * 4 + 3]};
+// HBM-bound (writes 64 channels per pixel: 256 B as planes or fp32).  Lane = (pixel of a quad, 8-channel group): the 72
+// weights + 8 biases of the channel group live in registers for the whole grid-stride loop, and a warp's store is 4 pixels x
+// 128 contiguous bytes per plane.
+constexpr int C1A_THREADS = 256;
+__global__ void __launch_bounds__(C1A_THREADS) k_conv1a(const uint8_t* __restrict__ gray, const float* __restrict__ wt /*[9][64]*/,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                                                         __half* __restrict__ oh, __half* __restrict__ ol) {
+  const int lane = threadIdx.x & 31, cg = lane & 7, sub = lane >> 3;
+  float w[9][8], b[8];
 #pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
+  for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      int yy = y + dy, xx = x + dx;
-      float v = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = (float)gray[(size_t)yy * W + xx] / 255.0f;
-      const float* wp = &ws[((dy + 1) * 3 + (dx + 1)) * 64 + cg * 4];
+    for (int c = 0; c < 8; ++c) w[tp][c] = __ldg(wt + tp * 64 + cg * 8 + c);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+  for (int c = 0; c < 8; ++c) b[c] = __ldg(bias + cg * 8 + c);
+  // a warp step = 4 consecutive pixels of one row: lanes 0..17 fetch and normalise the 3 x 6 input window once, every lane
+  // then picks its 9 taps by shuffle
+  const int qpr = (W + 3) / 4;  // quads per row
+  const long long nquad = (long long)H * qpr;
+  const long long warp0 = (long long)blockIdx.x * (C1A_THREADS / 32) + (threadIdx.x >> 5), nwarp = (long long)gridDim.x * (C1A_THREADS / 32);
+  const int wr = lane / 6, wc = lane % 6;  // window cell of lanes 0..17
+  for (long long q = warp0; q < nquad; q += nwarp) {
+    const int y = (int)(q / qpr), x0 = (int)(q % qpr) * 4;
+    const long long pix = (long long)y * W + x0 + sub;
+    float win = 0.f;
+    {
+      const int yy = y + wr - 1, xx = x0 + wc - 1;
+      if (lane < 18 && yy >= 0 && yy < H && xx >= 0 && xx < W) win = (float)__ldg(gray + (size_t)yy * W + xx) / 255.0f;
     }
-  }
-  float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-  if (oh) {  // split fp16 planes for the tcgen05 convolutions
-    uint32_t h01, l01, h23, l23;
-    tc::split2(o.x, o.y, h01, l01);
-    tc::split2(o.z, o.w, h23, l23);
-    *reinterpret_cast<uint2*>(oh + (size_t)pix * 64 + cg * 4) = make_uint2(h01, h23);
-    *reinterpret_cast<uint2*>(ol + (size_t)pix * 64 + cg * 4) = make_uint2(l01, l23);
-  } else {
-    *reinterpret_cast<float4*>(out + (size_t)pix * 64 + cg * 4) = o;
+    float2 acc2[4];  // packed pairs: FFMA2 = two IEEE fp32 FMAs per issue slot, same bits as scalar fmaf
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc2[c] = make_float2(b[2 * c], b[2 * c + 1]);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float v = __shfl_sync(0xffffffffu, win, dy * 6 + sub + dx);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          acc2[c] = tc::ffma2(make_float2(v, v), make_float2(w[dy * 3 + dx][2 * c], w[dy * 3 + dx][2 * c + 1]), acc2[c]);
+      }
+    }
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[2 * c] = fmaxf(acc2[c].x, 0.f), acc[2 * c + 1] = fmaxf(acc2[c].y, 0.f);
+    if (x0 + sub >= W) continue;
+    if (oh) {  // split fp16 planes for the tcgen05 convolutions
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc::split2(acc[2 * i], acc[2 * i + 1], hi[i], lo[i]);
+      *reinterpret_cast<uint4*>(oh + (size_t)pix * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(ol + (size_t)pix * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      float4* d = reinterpret_cast<float4*>(out + (size_t)pix * 64 + cg * 8);
+      d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
   }
 }
 
@@ -267,17 +295,45 @@ __global__ void __launch_bounds__(128) k_head_scores(const float* __restrict__ c
   }
 }
 
+// tcgen05 path of the two 1x1 heads: the channel mixing runs on k_gemm_ws (linear.cuh), these finish the job.
+// softmax over the 65 logits of a cell, drop the dustbin, depth-to-space (superpoint.py:162-166): one warp per cell.
+__global__ void __launch_bounds__(256) k_head_softmax(const float* __restrict__ logits, int ld, float* __restrict__ heat, int Hc, int Wc) {
+  const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= Hc * Wc) return;
+  const float* lg = logits + (size_t)cell * ld;
+  const float v0 = lg[lane], v1 = lg[lane + 32], v2 = lane == 0 ? lg[64] : -INFINITY;
+  const float m = warp_max(fmaxf(fmaxf(v0, v1), v2));
+  const float e0 = expf(v0 - m), e1 = expf(v1 - m), e2 = lane == 0 ? expf(v2 - m) : 0.f;
+  const float s = warp_sum(e0 + e1 + e2);
+  const int r = cell / Wc, cc = cell % Wc, W8 = Wc * 8;
+  heat[(size_t)(8 * r + (lane >> 3)) * W8 + 8 * cc + (lane & 7)] = e0 / s;  // channel k -> pixel (8r + k/8, 8c + k%8)
+  heat[(size_t)(8 * r + 4 + (lane >> 3)) * W8 + 8 * cc + (lane & 7)] = e1 / s;
+}
+// per-cell L2 normalisation of the dense descriptor map, in place (superpoint.py:192): one warp per cell
+__global__ void __launch_bounds__(256) k_head_l2norm(float* __restrict__ dense, int ncell) {
+  const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  float4* p = reinterpret_cast<float4*>(dense + (size_t)cell * 256);
+  float4 a = p[lane], b = p[lane + 32];
+  const float ss = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  p[lane] = make_float4(a.x / nrm, a.y / nrm, a.z / nrm, a.w / nrm);
+  p[lane + 32] = make_float4(b.x / nrm, b.y / nrm, b.z / nrm, b.w / nrm);
+}
+
 // simple_nms with radius 4 (superpoint.py:47-62), fused over a tile with a 20-pixel halo, followed by the
 // threshold + border test (superpoint.py:170-178) feeding per-row keypoint counts.
-constexpr int NT_W = 64, NT_H = 32, NR = 4, NHALO = 5 * NR;
-constexpr int NRW = NT_W + 2 * NHALO, NRH = NT_H + 2 * NHALO;  // 104 x 72 region = tile + the 20-px halo the five pools need
+// tile 64 x 40: a VGA score map is 10 x 12 = 120 tiles = ONE wave of 1-CTA-per-SM blocks (64 x 32 gave 150 tiles = two waves on
+// 148 SMs: half of the 47 us the kernel took was the second, 2-block wave)
+constexpr int NT_W = 64, NT_H = 40, NR = 4, NHALO = 5 * NR;
+constexpr int NRW = NT_W + 2 * NHALO, NRH = NT_H + 2 * NHALO;  // 104 x 80 region = tile + the 20-px halo the five pools need
 constexpr int NREG = NRW * NRH;
 // shared-memory planes carry a 4-cell sentinel frame (-inf for scores, 0 for masks) so that every 9-tap window is a fixed,
-// fully unrolled run of 9 loads with no bounds logic: pitch 112, 80 rows
+// fully unrolled run of 9 loads with no bounds logic: pitch 112, 88 rows
 constexpr int NPW = NRW + 2 * NR, NPH = NRH + 2 * NR;
 constexpr int NPLANE = NPW * NPH;
 constexpr int NMS_THREADS = 1024;
-__device__ __forceinline__ int nms_idx(int c) {  // region cell c (row-major 104 x 72) -> index inside a padded plane
+__device__ __forceinline__ int nms_idx(int c) {  // region cell c (row-major 104 x 80) -> index inside a padded plane
   const int y = c / NRW, x = c - y * NRW;
   return (y + NR) * NPW + x + NR;
 }
@@ -320,7 +376,7 @@ __device__ __forceinline__ void dilate9_b(const uint8_t* __restrict__ src, uint8
 }
 
 // simple_nms(scores, 4) (superpoint.py:47-62) fused with the threshold / border test and the per-row survivor counts: one
-// pass over a 64 x 32 tile whose 20-px halo makes the three rounds of 9 x 9 pools local.  1024 threads (32 warps hide the
+// pass over a 64 x 40 tile whose 20-px halo makes the three rounds of 9 x 9 pools local.  1024 threads (32 warps hide the
 // shared-memory latency of the unrolled 9-tap runs); float equality compares exactly as the reference does.
 __global__ void __launch_bounds__(NMS_THREADS) k_nms(const float* __restrict__ heat, float* __restrict__ nms, int H8, int W8,
                                                       float thr, int border, int* __restrict__ rowcnt) {
@@ -550,29 +606,55 @@ static int sp_conv3x3(b2_context* ctx, cudaStream_t st, const float* in, int li,
   return B2_OK;
 }
 
-// tcgen05 implicit-GEMM convolution on split-fp16 NHWC planes (conv_tma.cuh).  `in` / `out` buffers hold the hi plane
-// followed by the lo plane (+ pixels * channels halves).
+// tcgen05 implicit-GEMM convolution on split-fp16 NHWC planes (conv_ps.cuh: persistent, halo reuse, resident weights).
+// `in` / `out` buffers hold the hi plane followed by the lo plane (+ pixels * channels halves).
 static int sp_conv3x3_tc(b2_context* ctx, cudaStream_t st, const DevBuf& in, int li, int H, int W, bool pool, DevBuf* out_planes,
                          float* out_f32) {
   SuperPointState* s = ctx->sp;
   const int Cin = SP_CI[li], Cout = SP_CO[li];
   const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
-  ConvTmaMaps maps;
   const __half* ih = in.as<__half>();
   const __half* il = ih + (size_t)H * W * Cin;
   const __half* wh = s->wsplit_h.as<__half>() + s->wsoff[li];
   const __half* wl = s->wsplit_l.as<__half>() + s->wsoff[li];
-  bool ok = tma_map_nhwc(&maps.ah, ih, H, W, Cin) && tma_map_nhwc(&maps.al, il, H, W, Cin) &&
-            tma_map_2d(&maps.wh, wh, Cout, 9 * Cin, 9 * Cin, CV_N) && tma_map_2d(&maps.wl, wl, Cout, 9 * Cin, 9 * Cin, CV_N);
-  if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (conv)");
-  ConvTmaArgs a{};
+  SuperPointState::ConvMapCache& mc = s->conv_maps[li];  // the maps only change with the image size / a reallocation
+  if (mc.ih != ih || mc.wh != wh || mc.H != H || mc.W != W) {
+    bool ok = tma_map_nhwc_halo(&mc.maps.ah, ih, H, W, Cin) && tma_map_nhwc_halo(&mc.maps.al, il, H, W, Cin) &&
+              tma_map_2d(&mc.maps.wh, wh, Cout, 9 * Cin, 9 * Cin, 64) && tma_map_2d(&mc.maps.wl, wl, Cout, 9 * Cin, 9 * Cin, 64);
+    if (!ok) return b2_fail(ctx, B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (conv)");
+    mc.ih = ih, mc.wh = wh, mc.H = H, mc.W = W;
+  }
+  const ConvPsMaps& maps = mc.maps;
+  ConvPsArgs a{};
   a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.pool = pool ? 1 : 0, a.bias = s->b[li];
   if (out_planes) a.Oh = out_planes->as<__half>(), a.Ol = a.Oh + (size_t)OH * OW * Cout;
   a.Of = out_f32, a.err_flag = s->errflag.as<int>();
-  b2_prof_work(ctx, "k_conv_tma", 2.0 * 9.0 * H * W * Cin * Cout);
-  B2_LAUNCH(ctx, k_conv_tma, dim3(cdiv(W, CV_TW), cdiv(H, CV_TH), Cout / CV_N), 128, CV_SMEM, st, maps, a);
+  if (getenv("B2_CONV_DBG")) {  // profiling runs: per-CTA timestamps of layer li, read back through b2_debug_fetch("conv_dbg")
+    if (s->conv_dbg.ensure((size_t)12 * 148 * 8 * sizeof(float)) == cudaSuccess) {
+      a.dbg = s->conv_dbg.as<float>() + (size_t)li * 148 * 8;
+      ctx->debug["conv_dbg"] = {s->conv_dbg.as<float>(), (int64_t)12 * 148 * 8};
+    }
+  }
+  const int nblk = Cout / 64, units = cdiv(W, CP_TW) * cdiv(H, CP_TH) * nblk;
+  int grid = ctx->sm_count < units ? ctx->sm_count : units;
+  grid -= grid % nblk;  // a CTA keeps one 64-channel block of the weights resident: CTA c serves block c % nblk
+  b2_prof_work(ctx, "k_conv_ps", 2.0 * 9.0 * H * W * Cin * Cout);
+  B2_LAUNCH(ctx, k_conv_ps, grid, CP_THREADS, CP_SMEM, st, maps, a);
   B2_CHECK_LAUNCH(ctx);
   return B2_OK;
+}
+
+// 1x1 head (convPb / convDb) on the shared tcgen05 GEMM: out[cell][n] = sum_k in[cell][k] * W[n][k] + bias[n]  (fp32-equivalent)
+static int sp_head_gemm(b2_context* ctx, cudaStream_t st, const DevBuf& in_planes, int li, int cells, float* out, int ldc) {
+  SuperPointState* s = ctx->sp;
+  const int K = SP_CI[li], N = SP_CO[li];
+  TcWeights tw{nullptr, nullptr, nullptr, s->errflag.as<int>(), true};
+  tw.sm_count = ctx->sm_count;
+  LinArgs a;
+  a.a1p = {in_planes.as<__half>(), in_planes.as<__half>() + (size_t)cells * K}, a.lda1 = K, a.K1 = K;
+  a.bp = {s->wsplit_h.as<__half>() + s->wsoff[li], s->wsplit_l.as<__half>() + s->wsoff[li]}, a.ldb = K;
+  a.bias = s->b[li], a.cf = out, a.ldc = ldc, a.tc_want_f32 = true, a.M = cells, a.N = N;
+  return run_linear(ctx, st, tw, &a, 1);
 }
 
 static size_t nms_smem_bytes() { return (size_t)NPLANE * 4 * sizeof(float) + (size_t)NPLANE * 3; }
@@ -628,6 +710,7 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
     for (int l = 0; l < SP_NCONV; ++l) {
       s->wsoff[l] = tot;
       if (SP_K[l] == 3 && SP_CI[l] >= 64) tot += (size_t)SP_CO[l] * 9 * SP_CI[l];
+      if (SP_K[l] == 1) tot += (size_t)SP_CO[l] * SP_CI[l];  // 1x1 heads: [cout][cin], the checkpoint's own order
     }
     std::vector<float> stage(tot);
     size_t src2 = 0;
@@ -639,6 +722,8 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
         for (int o = 0; o < co; ++o)
           for (int tp = 0; tp < 9; ++tp)
             for (int i = 0; i < ci; ++i) d[(size_t)o * 9 * ci + tp * ci + i] = w[((size_t)o * ci + i) * 9 + tp];
+      } else if (SP_K[l] == 1) {
+        std::copy(blob + src2, blob + src2 + (size_t)co * ci, stage.data() + s->wsoff[l]);
       }
       src2 += (size_t)co * ci * kk + co;
     }
@@ -654,7 +739,8 @@ extern "C" int b2_superpoint_set_weights(b2_context* ctx, const float* blob, siz
     B2_CHECK_LAUNCH(ctx);
     B2_CUDA(ctx, cudaDeviceSynchronize());
     tmp.release();
-    B2_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
+    B2_CUDA(ctx, cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM));
+    B2_CUDA(ctx, cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
     s->use_tc = !b2_force_simt(ctx) && tma_encoder() != nullptr;
   }
   B2_CUDA(ctx, cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
@@ -698,7 +784,7 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   if (tcp) {
     B2_CUDA(ctx, featp.ensure((size_t)Hc * Wc * 128 * sizeof(float)));
     __half* p0 = s->a0.as<__half>();
-    B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, p0, p0 + px * 64);
+    B2_LAUNCH(ctx, k_conv1a, (unsigned)(ctx->sm_count * 8), C1A_THREADS, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, p0, p0 + px * 64);
     B2_CHECK_LAUNCH(ctx);
     // encoder (superpoint.py:148-158) as TMA-fed tcgen05 implicit GEMMs on split-fp16 planes; pools fused
     if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 1, H, W, true, &s->a1, nullptr))) return rc;      // conv1b + pool
@@ -708,9 +794,9 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
     if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 5, H4, W4, true, &s->a1, nullptr))) return rc;    // conv3b + pool
     if ((rc = sp_conv3x3_tc(ctx, st, s->a1, 6, Hc, Wc, false, &s->a0, nullptr))) return rc;   // conv4a
     if ((rc = sp_conv3x3_tc(ctx, st, s->a0, 7, Hc, Wc, false, &featp, feat))) return rc;      // conv4b (planes + fp32)
-    if ((rc = sp_conv3x3_tc(ctx, st, featp, 8, Hc, Wc, false, nullptr, head))) return rc;     // convPa -> fp32 for the score head
+    if ((rc = sp_conv3x3_tc(ctx, st, featp, 8, Hc, Wc, false, &s->head, nullptr))) return rc;  // convPa -> planes for the score head
   } else {
-  B2_LAUNCH(ctx, k_conv1a, (unsigned)((px + 15) / 16), 256, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, (__half*)nullptr,
+  B2_LAUNCH(ctx, k_conv1a, (unsigned)(ctx->sm_count * 8), C1A_THREADS, 0, st, s->gray.as<uint8_t>(), s->w[0], s->b[0], a0, H, W, (__half*)nullptr,
             (__half*)nullptr);
   B2_CHECK_LAUNCH(ctx);
   // encoder (superpoint.py:148-158); pools fused into conv1b / conv2b / conv3b
@@ -724,7 +810,13 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   // detector head (superpoint.py:161-167)
   if ((rc = sp_conv3x3(ctx, st, feat, 8, head, Hc, Wc, false))) return rc;  // convPa
   }
-  B2_LAUNCH(ctx, k_head_scores, cdiv(Hc * Wc, PB_CELLS), 128, 0, st, head, s->w[9], s->b[9], s->heat.as<float>(), Hc, Wc);
+  if (tcp) {  // convPb as a GEMM (65 logits per cell, row pitch 68), then softmax + depth-to-space
+    B2_CUDA(ctx, s->logits.ensure((size_t)Hc * Wc * 68 * sizeof(float)));
+    if ((rc = sp_head_gemm(ctx, st, s->head, 9, Hc * Wc, s->logits.as<float>(), 68))) return rc;
+    B2_LAUNCH(ctx, k_head_softmax, cdiv(Hc * Wc, 8), 256, 0, st, s->logits.as<float>(), 68, s->heat.as<float>(), Hc, Wc);
+  } else {
+    B2_LAUNCH(ctx, k_head_scores, cdiv(Hc * Wc, PB_CELLS), 128, 0, st, head, s->w[9], s->b[9], s->heat.as<float>(), Hc, Wc);
+  }
   B2_CHECK_LAUNCH(ctx);
   B2_CUDA(ctx, cudaMemsetAsync(s->rowcnt.p, 0, (size_t)(H8 + 1) * sizeof(int), st));
   B2_LAUNCH(ctx, k_nms, dim3(cdiv(W8, NT_W), cdiv(H8, NT_H)), NMS_THREADS, nms_smem_bytes(), st, s->heat.as<float>(),
@@ -737,9 +829,13 @@ static int sp_detect_impl(b2_context* ctx, const uint8_t* image, int H, int W, i
   B2_CHECK_LAUNCH(ctx);
   // descriptor head (superpoint.py:190-192): dense map stays resident for the describe stage
   if (tcp) {
-    if ((rc = sp_conv3x3_tc(ctx, st, featp, 10, Hc, Wc, false, nullptr, head))) return rc;  // convDa
-  } else if ((rc = sp_conv3x3(ctx, st, feat, 10, head, Hc, Wc, false))) return rc;  // convDa
-  B2_LAUNCH(ctx, k_head_desc, cdiv(Hc * Wc, DB_CELLS), 256, 0, st, head, s->w[11], s->b[11], s->dense.as<float>(), Hc * Wc);
+    if ((rc = sp_conv3x3_tc(ctx, st, featp, 10, Hc, Wc, false, &s->head, nullptr))) return rc;  // convDa -> planes
+    if ((rc = sp_head_gemm(ctx, st, s->head, 11, Hc * Wc, s->dense.as<float>(), 256))) return rc;  // convDb
+    B2_LAUNCH(ctx, k_head_l2norm, cdiv(Hc * Wc, 8), 256, 0, st, s->dense.as<float>(), Hc * Wc);
+  } else {
+    if ((rc = sp_conv3x3(ctx, st, feat, 10, head, Hc, Wc, false))) return rc;  // convDa
+    B2_LAUNCH(ctx, k_head_desc, cdiv(Hc * Wc, DB_CELLS), 256, 0, st, head, s->w[11], s->b[11], s->dense.as<float>(), Hc * Wc);
+  }
   B2_CHECK_LAUNCH(ctx);
   int n = 0;
   B2_CUDA(ctx, cudaMemcpyAsync(&n, s->rowoff.as<int>() + H8, sizeof(int), cudaMemcpyDeviceToHost, st));
