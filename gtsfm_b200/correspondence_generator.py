@@ -53,10 +53,19 @@ class B200CorrespondenceGenerator(_Base):
         if world > 1:
             paired = {i for p in visibility_graph for i in p}
             todo |= {i for i in range(len(images)) if i not in paired and i % world == rank}
+        plain: List[Tuple[int, torch.Tensor]] = []
         for idx in sorted(todo):
             img = images[idx].result() if hasattr(images[idx], "result") else images[idx]  # Dask Future or Image
             arr = img.value_array if hasattr(img, "value_array") else np.asarray(img)
-            feats[idx] = fe.detect(torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device), mask=getattr(img, "mask", None))
+            dev = torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device)
+            if getattr(img, "mask", None) is not None:
+                feats[idx] = fe.detect(dev, mask=img.mask)  # masks are applied on the host before the top-k: two-call path
+            else:
+                plain.append((idx, dev))
+        for c0 in range(0, len(plain), 32):  # unmasked images: enqueued 32 at a time, no synchronisation between images
+            chunk = plain[c0:c0 + 32]
+            for (idx, _), f in zip(chunk, fe.detect_many([d for _, d in chunk])):
+                feats[idx] = f
         local: Dict[Tuple[int, int], np.ndarray] = {}
         for c0 in range(0, len(mine), 8):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
             chunk = mine[c0:c0 + 8]

@@ -31,6 +31,7 @@ class DeviceFeatures:
         return int(self.kp.shape[0])
 
 
+DETECT_LANES = int(os.environ.get("B2_DETECT_LANES", "4"))  # concurrent SuperPoint instances used by detect_many
 RESERVE_SMS_FOR_VERIFY = int(os.environ.get("B2_RESERVE_SMS", "8"))  # k_rs_hyp_E keeps 16 x 64-thread CTAs busy for ~1 ms
 
 
@@ -46,6 +47,9 @@ class DeviceFrontEnd:
         self.prune_min = -1 if cpu_semantics else 1536
         self.fp16_attention = 1 if fp16_attention else 0  # opt-in: the reference's CUDA numerics (lightglue.py:116-121)
         blob = weights.pack_superpoint(weights.load_state_dict(superpoint_sd))
+        self._sp_blob = blob
+        self._lanes = []  # extra (context, stream) SuperPoint lanes of detect_many
+        self._counts = None
         self.ctx.check(self.lib.b2_superpoint_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superpoint_set_weights")
         if lightglue_sd is not None:
             blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
@@ -58,6 +62,24 @@ class DeviceFrontEnd:
         self._vctx: Optional[_lib.Context] = None
         self._vstream: Optional[torch.cuda.Stream] = None
         self._vpool = None
+
+    # measurement helpers over every context that runs SuperPoint / matcher kernels for this front end (bench.py)
+    def _all_ctx(self):
+        return [self.ctx] + [c for c, _ in self._lanes]
+
+    def launch_count(self) -> int:
+        return sum(c.launch_count() for c in self._all_ctx())
+
+    def profile_start(self, kernel_prefix: str) -> None:
+        for c in self._all_ctx():
+            c.profile_start(kernel_prefix)
+
+    def profile_stop(self):
+        ms, n, w = 0.0, 0, 0.0
+        for c in self._all_ctx():
+            a, b, d = c.profile_stop()
+            ms, n, w = ms + a, n + b, w + d
+        return ms, n, w
 
     def _stream(self):
         return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -99,6 +121,46 @@ class DeviceFrontEnd:
                                                 self._stream())
         self.ctx.check(rc, "superpoint_extract_dev")
         return DeviceFeatures(kp[: n.value], score[: n.value], desc[: n.value], (h, w))
+
+    def detect_many(self, images) -> list:
+        """`detect` for a list of images with every image enqueued before the first result is read: no host synchronisation
+        between images (b2_superpoint_extract_async_dev), one at the end (b2_superpoint_finish_dev).  Images alternate between
+        DETECT_LANES library contexts on as many streams, so one image's narrow kernels (80-CTA layers, the one-block top-k / scan) and
+        launch gaps are filled by the other's.  Same outputs as [detect(im) for im in images]."""
+        k = self.max_keypoints
+        if self._counts is None or self._counts.numel() < len(images):  # page-locked once, reused (cudaHostAlloc is slow)
+            self._counts = torch.zeros(max(64, len(images)), dtype=torch.int32).pin_memory()
+        counts = self._counts
+        outs = []
+        lanes = [(self.ctx, torch.cuda.current_stream(self.device))]
+        for j in range(1, min(DETECT_LANES, len(images))):
+            if len(self._lanes) < j:  # another SuperPoint instance (own work buffers) + its stream
+                ctx = _lib.Context(self.device.index or 0)
+                ctx.check(self.lib.b2_superpoint_set_weights(ctx.handle, _lib.ptr(self._sp_blob), self._sp_blob.size), "superpoint_set_weights")
+                self._lanes.append((ctx, torch.cuda.Stream(self.device)))
+            self._lanes[j - 1][1].wait_stream(lanes[0][1])  # the images were produced on the caller's stream
+            lanes.append(self._lanes[j - 1])
+        for i, image in enumerate(images):
+            assert image.dtype == torch.uint8 and image.is_cuda and image.is_contiguous()
+            ctx, stream = lanes[i % len(lanes)]
+            h, w = int(image.shape[0]), int(image.shape[1])
+            ch = 1 if image.dim() == 2 else int(image.shape[2])
+            with torch.cuda.stream(stream):  # allocate on the stream that writes them (caching-allocator stream safety)
+                kp = torch.empty((k, 2), dtype=torch.float32, device=self.device)
+                score = torch.empty(k, dtype=torch.float32, device=self.device)
+                desc = torch.empty((k, 256), dtype=torch.float32, device=self.device)
+            rc = self.lib.b2_superpoint_extract_async_dev(ctx.handle, _lib.ptr(image), h, w, ch, w * ch, KEYPOINT_THRESHOLD,
+                                                          NMS_RADIUS, REMOVE_BORDERS, k, _lib.ptr(kp), _lib.ptr(score), _lib.ptr(desc),
+                                                          _lib.C.c_void_p(counts.data_ptr() + 4 * i), _lib.C.c_void_p(stream.cuda_stream))
+            ctx.check(rc, "superpoint_extract_async_dev")
+            outs.append((kp, score, desc, (h, w)))
+        for ctx, stream in lanes:
+            ctx.check(self.lib.b2_superpoint_finish_dev(ctx.handle, _lib.C.c_void_p(stream.cuda_stream)), "superpoint_finish_dev")
+        for i, t in enumerate(outs):  # tensors written on a side stream are handed to the caller's stream
+            if i % len(lanes):
+                for x in t[:3]:
+                    x.record_stream(lanes[0][1])
+        return [DeviceFeatures(kp[:n], score[:n], desc[:n], hw) for (kp, score, desc, hw), n in zip(outs, counts[: len(images)].tolist())]
 
     def _detect_masked(self, image: torch.Tensor, h: int, w: int, ch: int, mask: np.ndarray) -> DeviceFeatures:
         cap = SuperPointEngine.capacity(h, w)

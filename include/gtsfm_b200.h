@@ -50,6 +50,8 @@ uint64_t b2_h2d_bytes(const b2_context* ctx);
  * "lightglue_batch" = 0..8: pairs per lock-step batch of b2_lightglue_match_batched_dev (0 = 8, the maximum).
  * "force_simt" = 0 | 1: models whose weights are set afterwards run the exact-fp32 SIMT kernels instead of the tcgen05
  * split-fp16 ones (the on-device cross-check of the tensor-core path; tests only).
+ * "superpoint_graph" = 0 (default) | 1: launch every kernel of the SuperPoint network directly / replay the ~21 launches as one
+ * CUDA graph per (image shape, parameters, buffers) key (measured slower on B200: the path is GPU-bound, not launch-bound).
  * "feature_cache" = 0 | 1: drop every cached device copy of host feature arrays and (0, default) copy on every call like the
  * reference / (1) keep device copies keyed by (host pointer, size) and validated by a hash of the FULL contents, so arrays
  * edited in place are re-sent.  Only pays off for callers that pass the same numpy buffers repeatedly (it does nothing for
@@ -93,6 +95,14 @@ int b2_superpoint_describe_dev(b2_context* ctx, uint64_t map_token, const float*
 int b2_superpoint_extract_dev(b2_context* ctx, const uint8_t* image, int height, int width, int channels, size_t pitch,
                               float keypoint_threshold, int nms_radius, int border, int max_keypoints, float* out_xy,
                               float* out_score, float* out_desc, int* out_n, void* stream);
+/* The same with NO host synchronisation, for callers that keep many images in flight: `out_n_pinned` (page-locked host int,
+ * one per image in flight) receives the keypoint count when `stream` gets there; the library's work buffers are reused in
+ * stream order.  Call b2_superpoint_finish_dev (stream synchronisation + tensor-core pipeline fault check) before reading the
+ * counts or the outputs on the host. */
+int b2_superpoint_extract_async_dev(b2_context* ctx, const uint8_t* image, int height, int width, int channels, size_t pitch,
+                                    float threshold, int nms_radius, int border, int max_keypoints, float* out_xy,
+                                    float* out_score, float* out_desc, int* out_n_pinned, void* stream);
+int b2_superpoint_finish_dev(b2_context* ctx, void* stream);
 /* Device top-k by score (k largest, ties broken by lower index), result kept in row-major order; writes the selected
  * indices (int32, ascending) and returns count in *out_k (HOST).  For the batched path; the per-call plugin uses the
  * reference's host argpartition to keep its index order. */

@@ -79,3 +79,25 @@ def test_batched_match_equals_per_pair_and_golden(b200_ctx, golden_dir):
                 fx = np.load(tag)
                 assert sb == int(fx["stop"]) and np.array_equal(mb.cpu().numpy(), fx["matches"])
         assert len(stops) >= 2 or profile == "prune", "the batch should mix stopping layers"
+
+
+def test_detect_many_and_graph_replay_equal_detect(b200_ctx):
+    """The no-sync multi-image path (b2_superpoint_extract_async_dev) and the opt-in CUDA-graph replay of the network give the
+    same features as one synchronous detect per image, on mixed image sizes (graph keys) and a flat image."""
+    sp_sd = syn.superpoint_state_dict(0)
+    frames, _ = syn.synthetic_sequence(4, 240, 320)
+    big, _ = syn.synthetic_sequence(2, 480, 640)
+    imgs = [torch.from_numpy(f).cuda() for f in (frames[0], big[0], frames[1], big[1], frames[2])]
+    imgs.append(torch.zeros((240, 320), dtype=torch.uint8, device="cuda"))  # flat image
+    fe = DeviceFrontEnd(sp_sd, None, max_keypoints=700, ctx=b200_ctx)
+    ref = [fe.detect(im) for im in imgs]
+    assert len(ref[1]) == 700 and 0 < len(ref[0]) <= 700
+    many = fe.detect_many(imgs)
+    b200_ctx.set_option("superpoint_graph", 1)
+    try:
+        graph = [fe.detect(im) for im in imgs] + fe.detect_many(imgs)
+    finally:
+        b200_ctx.set_option("superpoint_graph", 0)
+    for r, got in zip(ref * 3, many + graph):
+        assert len(got) == len(r) and got.shape == r.shape
+        assert torch.equal(got.kp, r.kp) and torch.equal(got.score, r.score) and torch.equal(got.desc, r.desc)
