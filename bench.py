@@ -467,26 +467,54 @@ def run_cuda(args):
             return B200SuperGlueMatcher(weights_path=sg_sd, device=local)
         return None
 
-    def e2e_run(cache: bool, steps: int):
-        mat = make_matcher(cache)
-        ver = B200Ransac(True, THR_PX, device=local) if w["verify"] else None
+    def e2e_run(cache: bool, steps: int, nthreads: int = 1):
+        """The step through the plugin classes with HOST buffers.  nthreads > 1: the step's plugin calls are issued from a pool
+        of host threads, each with its OWN plugin instances (own library context / stream), the way a GTSfM deployment issues
+        them from several Dask worker threads - one pair's copies, per-layer host syncs and latency-bound RANSAC kernels then
+        overlap another pair's matching on the GPU.  Same calls, same work, same host-in / host-out contract."""
+        import concurrent.futures as cf
+
+        tls = threading.local()
+        made, lock = [], threading.Lock()
+
+        def state():
+            if not hasattr(tls, "st"):
+                st = {"mat": make_matcher(cache), "ver": B200Ransac(True, THR_PX, device=local) if w["verify"] else None,
+                      "det": None if w["matcher"] else B200SuperPointDetectorDescriptor(max_keypoints=MAX_KP, weights_path=sp_sd, device=local)}
+                tls.st = st
+                with lock:
+                    made.append(st)
+            return tls.st
+
+        def do_pair(task):
+            pk, pd, kps, desc = task
+            st = state()
+            m = st["mat"].match(pk, kps, pd, desc, (H, W, 3), (H, W, 3))
+            if st["ver"] is not None:
+                st["ver"].verify(pk, kps, m, calib, calib)
+
+        def do_frame(idx):
+            state()["det"].detect_and_describe(Image(frames[idx % len(frames)]))
+
+        pool = cf.ThreadPoolExecutor(nthreads) if nthreads > 1 else None
+        run = (lambda fn, items: list(pool.map(fn, items))) if pool else (lambda fn, items: [fn(x) for x in items])
         hwin = deque(maxlen=max(LOOKAHEAD, 1))
         for i in range(LOOKAHEAD):
             hwin.append(det.detect_and_describe(Image(frames[i])))
 
         def step_host(c):
+            if not w["matcher"]:
+                run(do_frame, [c + j for j in range(NEW_FRAMES)])
+                return
             for j in range(NEW_FRAMES):
                 kps, desc = det.detect_and_describe(Image(frames[(c + j) % len(frames)]))
-                if mat is None:
-                    continue
-                for pk, pd in list(hwin):
-                    m = mat.match(pk, kps, pd, desc, (H, W, 3), (H, W, 3))
-                    if ver is not None:
-                        ver.verify(pk, kps, m, calib, calib)
+                run(do_pair, [(pk, pd, kps, desc) for pk, pd in list(hwin)])
                 hwin.append((kps, desc))
 
         def copied():
-            engs = [det._engine, mat._engine if mat else None, ver._engine if ver else None]
+            engs = [det._engine]
+            for st in made:
+                engs += [st["mat"]._engine if st["mat"] else None, st["ver"]._engine if st["ver"] else None, st["det"]._engine if st["det"] else None]
             return sum(e.h2d_bytes for e in engs if e), sum(e.d2h_bytes for e in engs if e)
 
         c2 = LOOKAHEAD
@@ -505,6 +533,8 @@ def run_cuda(args):
             wall += time.perf_counter() - t0
             c2 += NEW_FRAMES
         barrier()
+        if pool:
+            pool.shutdown()
         tt = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -514,9 +544,14 @@ def run_cuda(args):
     if args.no_e2e:
         e2e_value, h2d, d2h = float("nan"), 0, 0
     else:
-        e2e_value, h2d, d2h = e2e_run(False, args.steps)
+        e2e_value, h2d, d2h = e2e_run(False, args.steps, args.e2e_threads)
     e2e = {"value": e2e_value, "unit": "images/s" if not w["matcher"] else "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "host_threads": args.e2e_threads,
+           "host_threads_note": "plugin calls issued from this many host threads, each with its own plugin instances (what Dask worker threads do); "
+                                "single_thread = the same loop from one thread",
            "feature_cache": "off (default: every call uploads its arrays, like the reference)"}
+    if not args.no_e2e and args.e2e_threads > 1:
+        e2e["single_thread"] = e2e_run(False, max(1, args.steps - 1), 1)[0]
     if w["matcher"] == "lightglue" and not args.no_e2e:
         v2, h2, _ = e2e_run(True, max(1, args.steps - 1))
         e2e["with_feature_cache"] = {"value": v2, "h2d_bytes_per_step": int(h2), "note": "opt-in B200LightGlueMatcher(feature_cache=True), full-content hash"}
@@ -631,6 +666,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--frames", type=int, default=120, help="--scaling strong: frames of the fixed job (500 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads issuing the plugin calls of the e2e leg (each with its own plugin instances)")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the plugin-path leg (the line is then not a valid bench line)")
     ap.add_argument("--fp16-attention", action="store_true",
                     help="opt-in mode: the reference's CUDA numerics for attention (fp16 flash SDPA, one MMA per product); NOT the "
