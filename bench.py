@@ -338,6 +338,8 @@ def run_cuda(args):
     cursor = LOOKAHEAD
     stats = {"matches": 0, "inliers": 0, "pairs": 0, "stops": 0, "keypoints": 0, "frames": 0}
 
+    stats_lock = threading.Lock()
+
     def step_device(c):
         pending = []
         if not w["matcher"]:  # detect-describe only: every frame of the step enqueued before the first count is read
@@ -353,13 +355,17 @@ def run_cuda(args):
                 continue
             prevs = list(window)
             if w["matcher"] == "lightglue":
-                for b0 in range(0, len(prevs), MATCH_BATCH):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
-                    chunk = prevs[b0:b0 + MATCH_BATCH]
-                    for prev, (m, stop) in zip(chunk, fe.match_batch([(prev, f) for prev in chunk])):
-                        pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))  # overlaps the next batch's matcher kernels
-                        stats["matches"] += int(m.shape[0])
-                        stats["stops"] += stop
-                        stats["pairs"] += 1
+                # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev) over MATCH_LANES concurrent LightGlue instances;
+                # a batch's verifications are queued the moment it completes and overlap the other batches' matcher kernels
+                def on_chunk(c0, res, prevs=prevs, f=f):
+                    with stats_lock:
+                        for prev, (m, stop) in zip(prevs[c0:c0 + len(res)], res):
+                            pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))
+                            stats["matches"] += int(m.shape[0])
+                            stats["stops"] += stop
+                            stats["pairs"] += 1
+
+                fe.match_many([(prev, f) for prev in prevs], on_chunk=on_chunk)
             else:
                 for prev in prevs:
                     m = fe.match_superglue(prev, f)
@@ -424,10 +430,10 @@ def run_cuda(args):
     family_ms = {}
     if w["matcher"]:
         for fam in ("k_gemm_ws", "k_lg_", "k_sg_", "k_conv", "k_nms", "k_head"):
-            fe.ctx.profile_start(fam)
+            fe.profile_start(fam)
             step_device(cursor)
             torch.cuda.synchronize()
-            ms, n, _ = fe.ctx.profile_stop()
+            ms, n, _ = fe.profile_stop()
             if n:
                 family_ms[fam] = {"ms_per_step": ms, "launches": n}
         if fe._vctx is not None:
