@@ -63,6 +63,10 @@ SIGNATURES = {
     "b2_superglue_set_weights": (_i, [_vp, _vp, _sz]),
     "b2_superglue_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _ip, _vp]),
     "b2_superglue_match_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _ip]),
+    "b2_netvlad_blob_floats": (_sz, []),
+    "b2_netvlad_set_weights": (_i, [_vp, _vp, _sz]),
+    "b2_netvlad_describe_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b2_netvlad_describe_host": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "b2_similarity_pairs_host": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "b2_ransac_essential_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(RansacParams), _vp, _vp, _ip, _vp, _vp]),
     "b2_ransac_fundamental_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(RansacParams), _vp, _vp, _ip]),

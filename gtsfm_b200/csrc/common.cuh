@@ -83,6 +83,7 @@ struct LightGlueState;
 struct SuperGlueState;
 struct RansacState;
 struct RetrievalState;
+struct NetVladState;
 
 // Device copies of host feature arrays handed to the *_host matcher entry points.  GTSfM matches one image's (keypoints,
 // descriptors) against ~20-40 partners, always passing the same host arrays, so re-uploading 5 MB per image per pair is
@@ -116,6 +117,7 @@ struct b2_context {
   SuperGlueState* sg = nullptr;
   RansacState* rs = nullptr;
   RetrievalState* rt = nullptr;
+  NetVladState* nv = nullptr;
   // staging shared by the *_host entry points
   DevBuf stage_d[8];
   HostBuf stage_h[4];
@@ -178,6 +180,7 @@ void lg_destroy(b2_context* ctx);
 void sg_destroy(b2_context* ctx);
 void rs_destroy(b2_context* ctx);
 void rt_destroy(b2_context* ctx);
+void nv_destroy(b2_context* ctx);
 
 // shared device helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

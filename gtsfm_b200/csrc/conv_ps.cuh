@@ -45,6 +45,7 @@ struct ConvPsMaps {
 struct ConvPsArgs {
   int H, W, Cin, Cout;
   int pool;           // 1: 2x2/2 max-pool fused; output is (H/2, W/2)
+  int relu;           // 1: max(., 0) after the bias (every SuperPoint / VGG layer but NetVLAD's last convolution)
   const float* bias;  // [Cout]
   __half *Oh, *Ol;    // optional output planes NHWC
   float* Of;          // optional fp32 output NHWC
@@ -234,7 +235,7 @@ static __global__ void __launch_bounds__(CP_THREADS, 1) k_conv_ps(const __grid_c
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(a1[j], tc::LO_INV, a0[j]);
-        if (g.pool) {  // max over the 2x2 window: partners are lane ^ 1 (w) and lane ^ 8 (h); max commutes with bias + ReLU
+        if (g.pool) {  // max over the 2x2 window: partners are lane ^ 1 (w) and lane ^ 8 (h); max commutes with bias (+ ReLU)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
@@ -246,10 +247,11 @@ static __global__ void __launch_bounds__(CP_THREADS, 1) k_conv_ps(const __grid_c
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = __ldg(bp + j4);
-            v[4 * j4] = fmaxf(v[4 * j4] + b.x, 0.f);
-            v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b.y, 0.f);
-            v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b.z, 0.f);
-            v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b.w, 0.f);
+            v[4 * j4] += b.x, v[4 * j4 + 1] += b.y, v[4 * j4 + 2] += b.z, v[4 * j4 + 3] += b.w;
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (g.Of) {
             float4* d = reinterpret_cast<float4*>(g.Of + opix + cc * 32);

@@ -3,7 +3,7 @@
 // sim = G G^T of the global image descriptors (:93-157, torch.einsum on blocks of 50), then per query image the
 // `num_matched` best-scoring partners among j > i with score >= min_score (`pairs_from_score_matrix`, :232-260: invalid =
 // lower triangle + diagonal + below min_score -> -inf, torch.topk per row, finite entries kept in (row, rank) order).
-// The global-descriptor NETWORK (NetVLAD / MegaLoc) is not part of this library.
+// The global descriptors come from netvlad.cu (NetVLAD) or from the reference's own networks (MegaLoc).
 //
 // sim runs on the shared split-fp16 tcgen05 GEMM (fp32-equivalent); the selection is one warp per query row: `num_matched`
 // rounds of a warp arg-max over the row's valid entries strictly "after" the previous pick in (score desc, index asc) order.

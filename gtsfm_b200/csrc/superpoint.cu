@@ -645,7 +645,7 @@ static int sp_conv3x3_tc(b2_context* ctx, cudaStream_t st, const DevBuf& in, int
   }
   const ConvPsMaps& maps = mc.maps;
   ConvPsArgs a{};
-  a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.pool = pool ? 1 : 0, a.bias = s->b[li];
+  a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.pool = pool ? 1 : 0, a.relu = 1, a.bias = s->b[li];
   if (out_planes) a.Oh = out_planes->as<__half>(), a.Ol = a.Oh + (size_t)OH * OW * Cout;
   a.Of = out_f32, a.err_flag = s->errflag.as<int>();
   if (getenv("B2_CONV_DBG")) {  // profiling runs: per-CTA timestamps of layer li, read back through b2_debug_fetch("conv_dbg")

@@ -30,6 +30,10 @@ try:  # pragma: no cover - exercised only inside a full GTSfM environment
         from gtsfm.retriever.retriever_base import RetrieverBase
     except Exception:  # noqa: BLE001
         RetrieverBase = None
+    try:
+        from gtsfm.frontend.global_descriptor.global_descriptor_base import GlobalDescriptorBase
+    except Exception:  # noqa: BLE001
+        GlobalDescriptorBase = None
     HAVE_GTSFM = True
 except Exception:  # noqa: BLE001 - any import problem (gtsam, dask, hydra ...) means "not a GTSfM environment"
     HAVE_GTSFM = False
@@ -110,6 +114,7 @@ except Exception:  # noqa: BLE001 - any import problem (gtsam, dask, hydra ...) 
             ...
 
     RetrieverBase = None
+    GlobalDescriptorBase = None
 
     NUM_MATCHES_REQ_E_MATRIX = 5
     NUM_MATCHES_REQ_F_MATRIX = 8
@@ -207,3 +212,15 @@ if RetrieverBase is None:
 
         def save_diagnostics(self, image_fnames, pairs, plots_output_dir) -> None:
             return None
+
+
+if GlobalDescriptorBase is None:
+
+    class GlobalDescriptorBase:  # mirrors gtsfm/frontend/global_descriptor/global_descriptor_base.py:14-47
+        @abc.abstractmethod
+        def describe_batch(self, images):
+            ...
+
+        @abc.abstractmethod
+        def get_preprocessing_transforms(self):
+            ...

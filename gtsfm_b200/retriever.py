@@ -3,7 +3,7 @@
 Drop-in for gtsfm/retriever/similarity_retriever.py:35-182 (`SimilarityRetriever`): same constructor, `get_image_pairs`
 contract (ValueError without descriptors, RuntimeError above MAX_NUM_IMAGES, pairs (i1 < i2) per query image best first),
 `set_num_matched`, `repr`.  The similarity matrix G G^T and the per-row top-`num_matched` selection run in
-libgtsfm_b200.so (`b2_similarity_pairs_host`); the global-descriptor network (NetVLAD / MegaLoc) stays the reference's.
+libgtsfm_b200.so (`b2_similarity_pairs_host`); the descriptors come from `gtsfm_b200.global_descriptor` (NetVLAD) or the reference's.
 Difference: the returned similarity matrix is full (the reference fills the upper BLOCK triangle only, :104-111), which
 `compute_pairs_from_similarity_matrix` never looks at (:176-177 masks the lower triangle).
 """

@@ -161,6 +161,29 @@ def superglue_state_dict(seed: int = 1, profile: str = "full") -> Dict[str, np.n
     return sd
 
 
+NETVLAD_CONVS = [(0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256), (17, 256, 512),
+                 (19, 512, 512), (21, 512, 512), (24, 512, 512), (26, 512, 512), (28, 512, 512)]  # (index in backbone, Cin, Cout)
+NETVLAD_POOL_AFTER = (2, 7, 14, 21)  # backbone conv indices followed by MaxPool2d(2, 2) (vgg16.features[:-2])
+
+
+def netvlad_state_dict(seed: int = 3, whiten_dim: int = 4096) -> Dict[str, np.ndarray]:
+    """Seeded random weights with the exact tensor names / shapes of thirdparty/hloc/netvlad.py's NetVLAD module
+    (VGG16 features[:-2] backbone, NetVLADLayer(512, 64), whiten Linear(32768, 4096)) plus `mean` = the checkpoint's
+    `normalization.averageImage` (netvlad.py:157-160).  No checkpoint can be downloaded offline."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, np.ndarray] = {}
+    for idx, ci, co in NETVLAD_CONVS:
+        sd[f"backbone.{idx}.weight"] = (rng.standard_normal((co, ci, 3, 3)) * np.sqrt(2.0 / (9 * ci))).astype(np.float32)
+        sd[f"backbone.{idx}.bias"] = (0.05 * rng.standard_normal(co)).astype(np.float32)
+    sd["backbone.0.weight"] *= np.float32(1.0 / 60.0)  # the first layer sees mean-subtracted 0..255 pixels
+    sd["netvlad.score_proj.weight"] = (4.0 * rng.standard_normal((64, 512, 1))).astype(np.float32)
+    sd["netvlad.centers"] = rng.uniform(-0.08, 0.08, (512, 64)).astype(np.float32)
+    sd["whiten.weight"] = (rng.standard_normal((whiten_dim, 32768), dtype=np.float32) * np.float32(1.0 / np.sqrt(32768.0)))
+    sd["whiten.bias"] = (0.0005 * rng.standard_normal(whiten_dim)).astype(np.float32)
+    sd["mean"] = np.array([123.68, 116.779, 103.939], np.float32)
+    return sd
+
+
 def save_pth(state: Dict[str, np.ndarray], path) -> None:
     """Write a state dict in the reference's checkpoint format (torch.save of name -> tensor)."""
     import torch

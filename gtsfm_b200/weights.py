@@ -131,3 +131,40 @@ def superglue_head_major(sd: StateDict) -> StateDict:
 
 def pack_superglue(sd: StateDict) -> np.ndarray:
     return _pack(superglue_head_major(fold_superglue_batchnorm(sd)), SUPERGLUE_ORDER)
+
+
+# ---- NetVLAD (thirdparty/hloc/netvlad.py) ---------------------------------------------------------------------------------------
+NETVLAD_CONV_IDX = [0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28]  # Conv2d modules of vgg16.features[:-2]
+NETVLAD_ORDER: List[str] = ([f"backbone.{i}.{p}" for i in NETVLAD_CONV_IDX for p in ("weight", "bias")] +
+                            ["netvlad.score_proj.weight", "netvlad.centers", "whiten.weight", "whiten.bias", "mean"])
+
+
+def load_netvlad_mat(path: Union[str, Path]) -> StateDict:
+    """The MATLAB checkpoint the reference downloads (Pitts30K_struct.mat), parsed exactly as netvlad.py:115-160 does:
+    conv weights S x S x IN x OUT -> OUT x IN x S x S, score projection D x K -> K x D x 1, centres negated, whitening 1 x 1 x IN x OUT ->
+    OUT x IN, mean = net.meta.normalization.averageImage[0, 0].  (No checkpoint is available offline: exercised with the seeded
+    weights of `synthetic.netvlad_state_dict` only.)"""
+    import scipy.io
+
+    path = Path(path)
+    if not path.exists():
+        raise FileNotFoundError(f"weights not found at {path}")
+    mat = scipy.io.loadmat(str(path), struct_as_record=False, squeeze_me=True)
+    layers = mat["net"].layers
+    sd: StateDict = {}
+    conv_layers = [l for l in layers[:30] if hasattr(l, "weights") and np.ndim(l.weights[0]) == 4][:13]
+    for idx, l in zip(NETVLAD_CONV_IDX, conv_layers):
+        sd[f"backbone.{idx}.weight"] = np.ascontiguousarray(np.transpose(np.asarray(l.weights[0], np.float32), (3, 2, 0, 1)))
+        sd[f"backbone.{idx}.bias"] = np.asarray(l.weights[1], np.float32)
+    sd["netvlad.score_proj.weight"] = np.ascontiguousarray(np.asarray(layers[30].weights[0], np.float32).T)[:, :, None]
+    sd["netvlad.centers"] = -np.asarray(layers[30].weights[1], np.float32)
+    sd["whiten.weight"] = np.ascontiguousarray(np.asarray(layers[33].weights[0], np.float32).squeeze().T)
+    sd["whiten.bias"] = np.asarray(layers[33].weights[1], np.float32).squeeze()
+    sd["mean"] = np.asarray(mat["net"].meta.normalization.averageImage[0, 0], np.float32)
+    return sd
+
+
+def pack_netvlad(sd: StateDict) -> np.ndarray:
+    blob = _pack(sd, NETVLAD_ORDER)
+    assert blob.size == 14714688 + 2 * 64 * 512 + 4096 * 32768 + 4096 + 3, blob.size
+    return blob

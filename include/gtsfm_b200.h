@@ -219,11 +219,22 @@ int b2_ransac_essential_dev(b2_context* ctx, const float* kp1, const float* kp2,
 int b2_recover_pose_host(b2_context* ctx, const double* E, const double* x1, const double* x2, int k, double* out_R,
                          double* out_t, int* out_num_good);
 
+/* ---- NetVLAD global descriptor (gtsfm/frontend/global_descriptor/netvlad_global_descriptor.py:53-71,
+ * thirdparty/hloc/netvlad.py:52-75,163-193) ------------------------------------------------------------------------------------- */
+/* blob = 13 x (conv weight OIHW, bias) of VGG16 features[:-2], score_proj [64][512], centers [512][64], whitening weight
+ * [4096][32768] and bias [4096], mean [3] (the checkpoint's averageImage): b2_netvlad_blob_floats() floats. */
+size_t b2_netvlad_blob_floats(void);
+int b2_netvlad_set_weights(b2_context* ctx, const float* blob, size_t n_floats);
+/* images: [B][3][H][W] fp32 in [0, 1] (what the reference's batch transform produces), H, W >= 16; out: [B][4096] unit-norm
+ * descriptors.  _dev: device pointers, synchronises `stream` before returning; _host: host pointers. */
+int b2_netvlad_describe_dev(b2_context* ctx, const float* images, int batch, int height, int width, float* out, void* stream);
+int b2_netvlad_describe_host(b2_context* ctx, const float* images, int batch, int height, int width, float* out);
+
 /* ---- retrieval front ---------------------------------------------------------------- */
 /* gtsfm/retriever/similarity_retriever.py:86-260: sim = G G^T of the global image descriptors (desc: HOST [n][dim] fp32,
  * dim a multiple of 64), then per query image i its `num_matched` best partners among j > i with sim >= min_score, best
  * first.  out_partners: HOST [n][min(num_matched, n)] int32, -1 = no (further) partner; out_sim: HOST [n][n] or NULL.
- * (The descriptor network itself - NetVLAD / MegaLoc - is not part of this library.) */
+ * (Descriptors: b2_netvlad_describe_* above, or any other unit-norm global descriptor.) */
 int b2_similarity_pairs_host(b2_context* ctx, const float* desc, int n, int dim, int num_matched, float min_score,
                              int32_t* out_partners, float* out_sim);
 

@@ -364,6 +364,56 @@ def golden_retriever():
     np.savez_compressed(OUT / "retriever.npz", **out)
 
 
+def netvlad_images(shapes=((96, 128), (120, 168), (96, 128))):
+    """Seeded RGB frames as the (3, H, W) float32 [0, 1] tensors the reference's batch transform produces."""
+    return [np.ascontiguousarray(syn.synthetic_frame(40 + i, h, w).transpose(2, 0, 1)).astype(np.float32) / np.float32(255.0)
+            for i, (h, w) in enumerate(shapes)]
+
+
+def golden_netvlad():
+    """thirdparty/hloc/netvlad.py's NetVLAD.forward (unmodified) on seeded weights.  The constructor downloads and parses a
+    MATLAB checkpoint (netvlad.py:94-160), impossible offline, so the module is assembled exactly as :104-113 does - vgg16
+    features[:-2], NetVLADLayer(), Linear(32768, 4096) - and given `synthetic.netvlad_state_dict` instead."""
+    import torch.nn as nn
+    import torchvision.models as models
+
+    import types
+
+    class _Stub(types.ModuleType):  # dask is only imported by gtsfm.utils.logger; not installed offline
+        def __getattr__(self, n):
+            if n.startswith("__"):
+                raise AttributeError(n)
+            return type(n, (), {"__init__": lambda self, *a, **k: None})
+
+    for name in ("dask", "dask.distributed", "distributed"):
+        sys.modules.setdefault(name, _Stub(name))
+    sys.path.insert(0, "/root/reference")
+    from thirdparty.hloc.netvlad import NetVLAD, NetVLADLayer
+
+    sd = syn.netvlad_state_dict(3)
+    m = NetVLAD.__new__(NetVLAD)
+    nn.Module.__init__(m)
+    backbone = list(models.vgg16().children())[0]
+    m.backbone = nn.Sequential(*list(backbone.children())[:-2])
+    m.netvlad = NetVLADLayer()
+    m.whiten = nn.Linear(m.netvlad.output_dim, 4096)
+    missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items() if k != "mean"}, strict=True)
+    m.preprocess = {"mean": sd["mean"], "std": np.array([1, 1, 1], dtype=np.float32)}
+    m.eval()
+    out = {"versions": versions()}
+    imgs = netvlad_images()
+    with torch.no_grad():
+        for i, im in enumerate(imgs):
+            d = m({"image": torch.from_numpy(im)[None]})["global_descriptor"].numpy()[0]
+            out[f"desc_{i}"] = d
+            out[f"shape_{i}"] = np.asarray(im.shape[1:], np.int32)
+            print("netvlad", i, im.shape, float(np.linalg.norm(d)), d[:4])
+        both = m({"image": torch.from_numpy(np.stack([imgs[0], imgs[2]]))})["global_descriptor"].numpy()
+    out["desc_batch_0_2"] = both
+    print("missing keys:", missing, "cos(0,2) =", float(out["desc_0"] @ out["desc_2"]), "cos(0,1) =", float(out["desc_0"] @ out["desc_1"]))
+    np.savez_compressed(OUT / "netvlad.npz", **out)
+
+
 def main():
     assert ref_modules.available(), "/root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -382,6 +432,7 @@ def main():
     golden_superglue_large()
     golden_lund_door()
     golden_retriever()
+    golden_netvlad()
 
 
 if __name__ == "__main__":
