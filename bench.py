@@ -367,11 +367,13 @@ def run_cuda(args):
 
                 fe.match_many([(prev, f) for prev in prevs], on_chunk=on_chunk)
             else:
-                for prev in prevs:
-                    m = fe.match_superglue(prev, f)
-                    pending.append(fe.verify_async(prev, f, m, cal, cal, THR_PX))
-                    stats["matches"] += int(m.shape[0])
-                    stats["pairs"] += 1
+                def on_pair(i, m, prevs=prevs, f=f):  # a pair's verification is queued the moment its matches exist
+                    with stats_lock:
+                        pending.append(fe.verify_async(prevs[i], f, m, cal, cal, THR_PX))
+                        stats["matches"] += int(m.shape[0])
+                        stats["pairs"] += 1
+
+                fe.match_superglue_many([(prev, f) for prev in prevs], on_pair=on_pair)
             window.append(f)
         for fut in pending:  # every verification result is collected inside the step
             stats["inliers"] += fut.result()[3]
@@ -581,7 +583,10 @@ def run_cuda(args):
                          else ("CUDA events around every launch inside the timed pass" +
                                (f"; {DETECT_LANES} SuperPoint lanes run concurrently, so a launch shares the SMs with other lanes' kernels and "
                                 "the summed kernel time exceeds the step time (the kernel alone: profiles/r02_conv_ps_*.txt)"
-                                if not w["matcher"] and DETECT_LANES > 1 else "")),
+                                if not w["matcher"] and DETECT_LANES > 1 else
+                                "; 3 SuperGlue instances match pairs concurrently (match_superglue_many), so a launch shares the SMs with the other "
+                                "lanes' kernels: per-launch time, and with it this fraction, is inflated by the contention (one lane: 0.24)"
+                                if w["matcher"] == "superglue" else "")),
                          "note": "split-fp16 x3 products: tensor-pipe FLOPs are 3x the algorithmic FLOPs counted here (ceiling of frac = 0.33)"},
             "work": {"matches_per_pair": stats["matches"] / max(1, stats["pairs"]), "inliers_per_pair": stats["inliers"] / max(1, stats["pairs"]),
                      "mean_stop_layer": stats["stops"] / max(1, stats["pairs"]) if w["matcher"] == "lightglue" else None,

@@ -35,6 +35,9 @@ class DeviceFeatures:
 # concurrent LightGlue instances used by match_many.  Default 1: measured on B200 (40-pair steps of 5000 x 5000 keypoints) 215.8 /
 # 224.5 / 217.0 pairs/s with 1 / 2 / 3 lanes - the matcher's persistent kernels already fill the GPU, unlike SuperPoint's
 MATCH_LANES = int(os.environ.get("B2_MATCH_LANES", "1"))
+# concurrent SuperGlue instances used by match_superglue_many: 117.9 / 122.7 / 129.3 / 130.9 pairs/s with 1 / 2 / 3 / 4 lanes (B200,
+# 40-pair steps at 5000 keypoints, RANSAC on its own stream)
+SG_LANES = int(os.environ.get("B2_SG_LANES", "3"))
 DETECT_LANES = int(os.environ.get("B2_DETECT_LANES", "4"))  # concurrent SuperPoint instances used by detect_many
 RESERVE_SMS_FOR_VERIFY = int(os.environ.get("B2_RESERVE_SMS", "8"))  # k_rs_hyp_E keeps 16 x 64-thread CTAs busy for ~1 ms
 
@@ -63,8 +66,11 @@ class DeviceFrontEnd:
             blob = weights.pack_lightglue(weights.load_state_dict(lightglue_sd))
             self._lg_blob = blob
             self.ctx.check(self.lib.b2_lightglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "lightglue_set_weights")
+        self._sg_blob = None
+        self._sglanes = []  # (context, stream, executor) SuperGlue lanes of match_superglue_many (lane 0 = self.ctx)
         if superglue_sd is not None:
             blob = weights.pack_superglue(weights.load_state_dict(superglue_sd))
+            self._sg_blob = blob
             self.ctx.check(self.lib.b2_superglue_set_weights(self.ctx.handle, _lib.ptr(blob), blob.size), "superglue_set_weights")
         # verification runs on its own context + stream + host thread so that the (latency-bound, 16-CTA) RANSAC kernels of
         # pair p overlap the matcher kernels of pair p+1 (ctypes calls release the GIL)
@@ -75,7 +81,7 @@ class DeviceFrontEnd:
 
     # measurement helpers over every context that runs SuperPoint / matcher kernels for this front end (bench.py)
     def _all_ctx(self):
-        return [self.ctx] + [c for c, _ in self._lanes] + [l[0] for l in self._mlanes]
+        return [self.ctx] + [c for c, _ in self._lanes] + [l[0] for l in self._mlanes] + [l[0] for l in self._sglanes[1:]]
 
     def launch_count(self) -> int:
         return sum(c.launch_count() for c in self._all_ctx())
@@ -205,15 +211,64 @@ class DeviceFrontEnd:
         self.ctx.check(rc, "lightglue_match_dev")
         return out[: k.value], stop.value
 
-    def match_superglue(self, a: DeviceFeatures, b: DeviceFeatures, sinkhorn_iters: int = 20, match_threshold: float = 0.2) -> torch.Tensor:
+    def match_superglue_many(self, pairs: Sequence[Tuple[DeviceFeatures, DeviceFeatures]], on_pair=None, **kw) -> List[torch.Tensor]:
+        """`match_superglue` over a list of pairs, dealt round-robin to SG_LANES library contexts (own SuperGlue instance, stream
+        and host thread each): SuperGlue runs pair by pair with many narrow kernels (2000-keypoint GNN layers, one-block
+        filters), which concurrent pairs fill.  `on_pair(index, matches)` is called from the lane's thread as a pair completes."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        lanes = min(SG_LANES, len(pairs))
+        if lanes <= 1:
+            out = []
+            for i, (a, b) in enumerate(pairs):
+                m = self.match_superglue(a, b, **kw)
+                if on_pair:
+                    on_pair(i, m)
+                out.append(m)
+            return out
+        while len(self._sglanes) < lanes:  # lane 0 included: every lane has its own host thread
+            if not self._sglanes:
+                ctx = self.ctx
+            else:
+                ctx = _lib.Context(self.device.index or 0)
+                ctx.check(self.lib.b2_superglue_set_weights(ctx.handle, _lib.ptr(self._sg_blob), self._sg_blob.size), "superglue_set_weights")
+                ctx.set_option("reserve_sms", self._reserve_sms)
+            self._sglanes.append((ctx, torch.cuda.Stream(self.device) if self._sglanes else None, ThreadPoolExecutor(max_workers=1)))
+        main = torch.cuda.current_stream(self.device)
+
+        def work(lane, idxs):
+            ctx, stream, _ = self._sglanes[lane]
+            res = []
+            with torch.cuda.stream(stream if stream is not None else main):
+                for i in idxs:
+                    m = self.match_superglue(*pairs[i], ctx=ctx, **kw)
+                    if stream is not None:
+                        m.record_stream(main)
+                    if on_pair:
+                        on_pair(i, m)
+                    res.append((i, m))
+            return res
+
+        for _, stream, _ in self._sglanes[1:lanes]:
+            stream.wait_stream(main)  # the features were produced on the caller's stream
+        futs = [self._sglanes[l][2].submit(work, l, list(range(l, len(pairs), lanes))) for l in range(lanes)]
+        out: List[Optional[torch.Tensor]] = [None] * len(pairs)
+        for f in futs:
+            for i, m in f.result():
+                out[i] = m
+        return out  # type: ignore[return-value]
+
+    def match_superglue(self, a: DeviceFeatures, b: DeviceFeatures, sinkhorn_iters: int = 20, match_threshold: float = 0.2,
+                        ctx: Optional[_lib.Context] = None) -> torch.Tensor:
         """SuperGlue on device-resident features -> (k, 2) int64 device tensor (rows (i, matches0[i]) ascending in i)."""
         cap = max(1, min(len(a), len(b)))
         out = torch.empty((cap, 2), dtype=torch.int32, device=self.device)  # the ABI writes uint32 rows
         k = _lib.C.c_int(0)
-        rc = self.lib.b2_superglue_match_dev(self.ctx.handle, _lib.ptr(a.kp), _lib.ptr(a.score), _lib.ptr(a.desc), len(a), a.shape[0], a.shape[1],
+        ctx = ctx or self.ctx
+        rc = self.lib.b2_superglue_match_dev(ctx.handle, _lib.ptr(a.kp), _lib.ptr(a.score), _lib.ptr(a.desc), len(a), a.shape[0], a.shape[1],
                                              _lib.ptr(b.kp), _lib.ptr(b.score), _lib.ptr(b.desc), len(b), b.shape[0], b.shape[1],
                                              int(sinkhorn_iters), float(match_threshold), _lib.ptr(out), None, _lib.C.byref(k), self._stream())
-        self.ctx.check(rc, "superglue_match_dev")
+        ctx.check(rc, "superglue_match_dev")
         return out[: k.value].to(torch.int64)
 
     def match_many(self, pairs: Sequence[Tuple[DeviceFeatures, DeviceFeatures]], on_chunk=None, **kw) -> List[Tuple[torch.Tensor, int]]:
@@ -309,7 +364,7 @@ class DeviceFrontEnd:
             # the matcher's persistent kernels (one CTA per SM) leave a few SMs to the concurrent RANSAC kernels: a CTA
             # that finds its SM occupied would wait for a whole CTA lifetime and double the kernel's duration
             self._reserve_sms = RESERVE_SMS_FOR_VERIFY
-            for c in [self.ctx] + [l[0] for l in self._mlanes]:
+            for c in [self.ctx] + [l[0] for l in self._mlanes] + [l[0] for l in self._sglanes[1:]]:
                 c.set_option("reserve_sms", RESERVE_SMS_FOR_VERIFY)
 
     def verify(self, a: DeviceFeatures, b: DeviceFeatures, matches: torch.Tensor, cal1: Sequence[float], cal2: Sequence[float],
