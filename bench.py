@@ -15,7 +15,7 @@ Workloads (config.workload):
   superpoint_only configs[1]: SuperPoint detect + describe only, 640x480.  STEP = 32 frames; metric = images/s.
   small_stop      launch-bound regime: 1024 keypoints, 'stop' weights (early exit at layer 4-5, pruning on).  STEP = 40 pairs.
 Pairs shard across GPUs with no data-path collective (one weight broadcast at start-up); per-GPU work is fixed => "weak" scaling.
-`--scaling strong` instead times one fixed job (F frames, lookahead 20) through B200CorrespondenceGenerator + B200TwoViewBatch,
+`--scaling strong` instead times one fixed job (F frames, lookahead 20) through B200CorrespondenceGenerator (two-view verification run under the matching),
 including image (re-)detection on every rank and the final gather, wall-clock on rank 0.
 
 `value` times the device-resident path (frames already in HBM, features / matches stay in HBM, only per-pair scalars come back);
@@ -605,15 +605,14 @@ def run_cuda(args):
 
 def run_strong(args):
     """One fixed job through the real L2 seam: F frames, Sequential(lookahead 20) pairs, B200CorrespondenceGenerator (every rank
-    detects the images its pairs reference, matches its p mod world shard in batches of 8, all_gather_object of the results) followed by
-    B200TwoViewBatch over the same shard.  Wall-clock on rank 0 between two barriers; total work is fixed => "strong"."""
+    detects the images its pairs reference, matches its p mod world shard in batches of 8 with each batch's two-view verification queued
+    on the verification stream as it completes, all_gather_object of the match arrays).  Wall-clock on rank 0 between two barriers; total work is fixed => "strong"."""
     import torch
     import torch.distributed as dist
 
     from gtsfm_b200 import distributed as D, synthetic as syn
     from gtsfm_b200.correspondence_generator import B200CorrespondenceGenerator
     from gtsfm_b200.gtsfm_api import Image
-    from gtsfm_b200.two_view import B200TwoViewBatch
 
     rank, world, local, dev = _setup_dist()
     F, L = args.frames, 20
@@ -621,7 +620,8 @@ def run_strong(args):
     images = [Image(f) for f in frames]
     graph = [(i, j) for i in range(F) for j in range(i + 1, min(F, i + L + 1))]  # sequential_retriever.py:57-59
     gen = B200CorrespondenceGenerator(syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "bench"), max_keypoints=5000, device=local)
-    gen.generate_correspondences(None, images[:4], [(0, 1), (1, 2), (2, 3)])  # warm-up: contexts, workspaces, NCCL
+    warm = [(i, j) for i in range(6) for j in range(i + 1, 6)]  # warm-up: contexts, 8-pair workspaces, verification lane, NCCL
+    gen.generate_correspondences(None, images[:6], warm, verify_with=({i: cal for i in range(6)}, THR_PX))
 
     def barrier():
         if world > 1:
@@ -630,13 +630,11 @@ def run_strong(args):
 
     barrier()
     t0 = time.perf_counter()
-    kps, matches = gen.generate_correspondences(None, images, graph)
+    kps, matches = gen.generate_correspondences(None, images, graph, verify_with=({i: cal for i in range(F)}, THR_PX))
     t_corr = time.perf_counter() - t0
     fe = gen._front_end()
-    mine = D.shard_pairs(graph, rank, world)
     feats = gen.last_device_features
-    put = {p: torch.from_numpy(matches[p]).to(dev) for p in mine}
-    res = B200TwoViewBatch(fe, THR_PX).run(feats, mine, {i: cal for i in range(F)}, putative=put)
+    res = gen.last_two_view  # this rank's shard, verified under the matching (B200TwoViewBatch semantics)
     n_ok = sum(1 for r in res.values() if r.i2Ri1 is not None)
     barrier()
     wall = time.perf_counter() - t0
@@ -652,13 +650,13 @@ def run_strong(args):
     if rank == 0:
         cfg = config_of("vga_lightglue")
         cfg["workload"] = (f"strong scaling: ONE job of {F} synthetic 640x480 frames, Sequential lookahead 20 = {len(graph)} pairs (BASELINE configs[3] shape; "
-                           f"F = 500 gives its 9 790-pair graph), B200CorrespondenceGenerator + B200TwoViewBatch, pairs sharded p mod world")
+                           f"F = 500 gives its 9 790-pair graph), B200CorrespondenceGenerator with the two-view verification run under the matching, pairs sharded p mod world")
         line = {
             "metric": "image_pairs_per_sec", "value": len(graph) / wall, "unit": "pairs/s", "n_gpus": world, "steps": 1, "warmup": 1,
             "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "gpu_launches": int(fe.launch_count()),
             "strong": {"pairs": len(graph), "frames": F, "wall_s": wall, "correspondence_s_max_rank": t_corr,
-                       "detections_summed_over_ranks": det_total, "detections_if_not_duplicated": F, "verified_pairs": ok_total,
+                       "phases_rank0_s": gen.last_timing, "detections_summed_over_ranks": det_total, "detections_if_not_duplicated": F, "verified_pairs": ok_total,
                        "limits": "every rank re-detects the images its shard references (p mod world touches ~all frames), and the final "
                                  "all_gather_object pickles every (K, 2) match array to every rank"},
         }

@@ -28,11 +28,13 @@ class B200CorrespondenceGenerator(_Base):
         self._max_keypoints, self._device, self._cpu_semantics = max_keypoints, device, cpu_semantics
         self._fe: Optional[DeviceFrontEnd] = None
         self.last_device_features: Dict[int, DeviceFeatures] = {}  # device-resident features of the last call (for the two-view seam)
+        self.last_two_view: Dict[Tuple[int, int], object] = {}  # {pair: TwoViewResult} of the last call with verify_with
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_fe"] = None
         st["last_device_features"] = {}
+        st["last_two_view"] = {}
         return st
 
     def _front_end(self) -> DeviceFrontEnd:
@@ -41,8 +43,15 @@ class B200CorrespondenceGenerator(_Base):
                                       cpu_semantics=self._cpu_semantics)
         return self._fe
 
-    def generate_correspondences(self, client, images: Sequence, visibility_graph: Sequence[Tuple[int, int]]):
-        """-> (List[Keypoints] per image, Dict[(i1, i2), (K, 2) int64 match rows])."""
+    def generate_correspondences(self, client, images: Sequence, visibility_graph: Sequence[Tuple[int, int]], verify_with=None):
+        """-> (List[Keypoints] per image, Dict[(i1, i2), (K, 2) int64 match rows]).
+
+        `verify_with = (intrinsics {image: (f, u0, v0)}, threshold_px)` additionally runs the two-view verification of this
+        rank's pairs (gtsfm/two_view_estimator.py:350-481) UNDER the matching - a batch's RANSAC is queued on the verification
+        stream the moment its matches exist - and leaves {pair: TwoViewResult} in `self.last_two_view`."""
+        import time
+
+        t_start = time.perf_counter()
         fe = self._front_end()
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
@@ -66,11 +75,32 @@ class B200CorrespondenceGenerator(_Base):
             chunk = plain[c0:c0 + 32]
             for (idx, _), f in zip(chunk, fe.detect_many([d for _, d in chunk])):
                 feats[idx] = f
+        t_detect = time.perf_counter()
         local: Dict[Tuple[int, int], np.ndarray] = {}
-        for c0 in range(0, len(mine), 8):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev)
-            chunk = mine[c0:c0 + 8]
-            for (i1, i2), (m, _) in zip(chunk, fe.match_batch([(feats[i1], feats[i2]) for i1, i2 in chunk])):
-                local[(i1, i2)] = m.cpu().numpy()
+        pending = []
+
+        def on_chunk(c0, res):  # lock-step batches of 8 pairs (b2_lightglue_match_batched_dev), in completion order
+            for (i1, i2), (m, _) in zip(mine[c0:c0 + len(res)], res):
+                if verify_with is not None and int(m.shape[0]) >= 6:
+                    intr, thr = verify_with
+                    pending.append(((i1, i2), m, fe.verify_async(feats[i1], feats[i2], m, intr[i1], intr[i2], thr)))
+                elif verify_with is not None:
+                    pending.append(((i1, i2), m, None))
+
+        matched = fe.match_many([(feats[i1], feats[i2]) for i1, i2 in mine], on_chunk=on_chunk)
+        t_match = time.perf_counter()
+        for (i1, i2), (m, _) in zip(mine, matched):
+            local[(i1, i2)] = m.cpu().numpy()
+        if verify_with is not None:
+            from .two_view import B200TwoViewBatch, _failure
+
+            self.last_two_view = {}
+            for item in pending:
+                if item[2] is None:
+                    self.last_two_view[item[0]] = _failure(int(item[1].shape[0]))
+                else:
+                    B200TwoViewBatch._collect(item, self.last_two_view)
+        t_verify = time.perf_counter()
         self.last_device_features = feats
         matches = D.gather_pair_results(local)
         keypoints: List[Optional[Keypoints]] = [None] * len(images)
@@ -83,4 +113,7 @@ class B200CorrespondenceGenerator(_Base):
                 for i, k in part.items():
                     if keypoints[i] is None:  # (an empty Keypoints is falsy: test identity, not truth)
                         keypoints[i] = k
+        t_end = time.perf_counter()
+        self.last_timing = {"detect_s": t_detect - t_start, "match_s": t_match - t_detect, "collect_verify_s": t_verify - t_match,
+                            "gather_s": t_end - t_verify}  # where a call's wall time went (bench.py --scaling strong reports it)
         return keypoints, matches

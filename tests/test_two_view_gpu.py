@@ -82,3 +82,28 @@ def test_too_few_matches_is_the_failure_tuple():
     put = {(0, 1): torch.zeros((3, 2), dtype=torch.int64, device="cuda")}
     r = B200TwoViewBatch(fe).run(feats, [(0, 1)], {0: cal, 1: cal}, putative=put)[(0, 1)]
     assert r.i2Ri1 is None and r.i2Ui1 is None and r.v_corr_idxs.shape == (0, 2) and r.num_putative == 3
+
+
+def test_generator_verify_with_equals_two_view_batch():
+    """generate_correspondences(..., verify_with=...) = the same matches + the TwoViewResults B200TwoViewBatch gives for them."""
+    from gtsfm_b200.correspondence_generator import B200CorrespondenceGenerator
+    from gtsfm_b200.gtsfm_api import Image
+
+    frames, cal = syn.synthetic_sequence(6, 240, 320)
+    graph = [(i, j) for i in range(6) for j in range(i + 1, min(6, i + 4))]  # 12 pairs = two lock-step batches
+    gen = B200CorrespondenceGenerator(syn.superpoint_state_dict(0), syn.lightglue_state_dict(2, "sharp"), max_keypoints=600)
+    intr = {i: cal for i in range(6)}
+    kps, matches = gen.generate_correspondences(None, [Image(f) for f in frames], graph, verify_with=(intr, 4.0))
+    got = gen.last_two_view
+    fe, feats = gen._front_end(), gen.last_device_features
+    put = {p: torch.from_numpy(matches[p]).cuda() for p in graph}
+    want = B200TwoViewBatch(fe, 4.0).run(feats, graph, intr, putative=put)
+    assert set(got) == set(graph) and sum(1 for r in got.values() if r.i2Ri1 is not None) >= 10
+    for p in graph:
+        a, b = got[p], want[p]
+        assert a.num_putative == b.num_putative == len(matches[p]) and np.array_equal(a.v_corr_idxs, b.v_corr_idxs)
+        assert a.inlier_ratio_est_model == b.inlier_ratio_est_model
+        if b.i2Ri1 is None:
+            assert a.i2Ri1 is None
+        else:
+            assert np.array_equal(a.i2Ri1.matrix(), b.i2Ri1.matrix()) and np.array_equal(a.i2Ui1.point3(), b.i2Ui1.point3())
