@@ -604,8 +604,8 @@ def run_cuda(args):
 
 
 def run_strong(args):
-    """One fixed job through the real L2 seam: F frames, Sequential(lookahead 20) pairs, B200CorrespondenceGenerator (every rank
-    detects the images its pairs reference, matches its p mod world shard in batches of 8 with each batch's two-view verification queued
+    """One fixed job through the real L2 seam: F frames, Sequential(lookahead 20) pairs, B200CorrespondenceGenerator (every image
+    detected on one rank and its features all-gathered over NCCL, every rank matches its p mod world shard in batches of 8 with each batch's two-view verification queued
     on the verification stream as it completes, all_gather_object of the match arrays).  Wall-clock on rank 0 between two barriers; total work is fixed => "strong"."""
     import torch
     import torch.distributed as dist
@@ -638,7 +638,7 @@ def run_strong(args):
     n_ok = sum(1 for r in res.values() if r.i2Ri1 is not None)
     barrier()
     wall = time.perf_counter() - t0
-    tt = torch.tensor([wall, t_corr, float(len(feats)), float(n_ok)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([wall, t_corr, float(gen.last_detections), float(n_ok)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -646,7 +646,7 @@ def run_strong(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         wall, t_corr, det_total, ok_total = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
     else:
-        det_total, ok_total = float(len(feats)), float(n_ok)
+        det_total, ok_total = float(gen.last_detections), float(n_ok)
     if rank == 0:
         cfg = config_of("vga_lightglue")
         cfg["workload"] = (f"strong scaling: ONE job of {F} synthetic 640x480 frames, Sequential lookahead 20 = {len(graph)} pairs (BASELINE configs[3] shape; "
@@ -657,8 +657,10 @@ def run_strong(args):
             "config": cfg, "gpu_launches": int(fe.launch_count()),
             "strong": {"pairs": len(graph), "frames": F, "wall_s": wall, "correspondence_s_max_rank": t_corr,
                        "phases_rank0_s": gen.last_timing, "detections_summed_over_ranks": det_total, "detections_if_not_duplicated": F, "verified_pairs": ok_total,
-                       "limits": "every rank re-detects the images its shard references (p mod world touches ~all frames), and the final "
-                                 "all_gather_object pickles every (K, 2) match array to every rank"},
+                       "exchange": "each image detected on one rank (position mod world), features all-gathered over NCCL once; matches "
+                                   "all_gather_object'ed at the end",
+                       "limits": "what does not shrink with the number of GPUs: the feature all-gather (5 MB per image to every rank), the final "
+                                 "all_gather_object that pickles every (K, 2) match array to every rank, host-side result conversion"},
         }
         print(json.dumps(line))
     if world > 1:

@@ -28,6 +28,7 @@ class B200CorrespondenceGenerator(_Base):
         self._max_keypoints, self._device, self._cpu_semantics = max_keypoints, device, cpu_semantics
         self._fe: Optional[DeviceFrontEnd] = None
         self.last_device_features: Dict[int, DeviceFeatures] = {}  # device-resident features of the last call (for the two-view seam)
+        self.last_detections = 0  # images this rank detected in the last call
         self.last_two_view: Dict[Tuple[int, int], object] = {}  # {pair: TwoViewResult} of the last call with verify_with
 
     def __getstate__(self):
@@ -57,24 +58,56 @@ class B200CorrespondenceGenerator(_Base):
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         mine = D.shard_pairs(list(visibility_graph), rank, world)
         feats: Dict[int, DeviceFeatures] = {}
-        # images of this rank's pairs, plus (so that every image gets keypoints) images no pair references: idx mod world
-        todo = set(range(len(images))) if world == 1 else set(D.images_needed(mine))
-        if world > 1:
-            paired = {i for p in visibility_graph for i in p}
-            todo |= {i for i in range(len(images)) if i not in paired and i % world == rank}
-        plain: List[Tuple[int, torch.Tensor]] = []
-        for idx in sorted(todo):
+
+        def host_image(idx):
             img = images[idx].result() if hasattr(images[idx], "result") else images[idx]  # Dask Future or Image
-            arr = img.value_array if hasattr(img, "value_array") else np.asarray(img)
-            dev = torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device)
-            if getattr(img, "mask", None) is not None:
-                feats[idx] = fe.detect(dev, mask=img.mask)  # masks are applied on the host before the top-k: two-call path
+            return img, (img.value_array if hasattr(img, "value_array") else np.asarray(img))
+
+        masked = any(getattr(im, "mask", None) is not None for im in images if not hasattr(im, "result"))
+        if world > 1 and not masked:
+            # ONE job over several GPUs: every image is detected on exactly one rank (position mod world) and the features are
+            # exchanged with one all-gather over NVLink (5 MB per image) - re-detecting on every rank whose pairs touch an image
+            # made detection the part of the job that did not scale
+            k = fe.max_keypoints
+            n_loc = (len(images) + world - 1) // world
+            own = [i for i in range(len(images)) if D.image_owner(i, world) == rank]
+            devs = [torch.from_numpy(np.ascontiguousarray(host_image(i)[1])).to(fe.device) for i in own]
+            if devs:
+                kp_l, sc_l, de_l, cnt, shapes = fe.detect_pool(devs, slots=n_loc)
             else:
-                plain.append((idx, dev))
-        for c0 in range(0, len(plain), 32):  # unmasked images: enqueued 32 at a time, no synchronisation between images
-            chunk = plain[c0:c0 + 32]
-            for (idx, _), f in zip(chunk, fe.detect_many([d for _, d in chunk])):
-                feats[idx] = f
+                kp_l = torch.empty((n_loc, k, 2), dtype=torch.float32, device=fe.device)
+                sc_l = torch.empty((n_loc, k), dtype=torch.float32, device=fe.device)
+                de_l = torch.empty((n_loc, k, 256), dtype=torch.float32, device=fe.device)
+                cnt, shapes = [], []
+            meta = torch.zeros((n_loc, 3), dtype=torch.int32, device=fe.device)  # (count, height, width) per slot
+            if cnt:
+                meta[: len(cnt)] = torch.tensor([[c, h, w] for c, (h, w) in zip(cnt, shapes)], dtype=torch.int32)
+            kp_a, sc_a, de_a, meta_a = D.all_gather_features(kp_l, sc_l, de_l, meta)
+            meta_h = meta_a.cpu().tolist()
+            for i in range(len(images)):
+                slot = D.image_owner(i, world) * n_loc + i // world
+                c, h, w = meta_h[slot]
+                feats[i] = DeviceFeatures(kp_a[slot, :c], sc_a[slot, :c], de_a[slot, :c], (h, w))
+            self.last_detections = len(own)
+        else:
+            # images of this rank's pairs, plus (so that every image gets keypoints) images no pair references: idx mod world
+            todo = set(range(len(images))) if world == 1 else set(D.images_needed(mine))
+            if world > 1:
+                paired = {i for p in visibility_graph for i in p}
+                todo |= {i for i in range(len(images)) if i not in paired and i % world == rank}
+            plain: List[Tuple[int, torch.Tensor]] = []
+            for idx in sorted(todo):
+                img, arr = host_image(idx)
+                dev = torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device)
+                if getattr(img, "mask", None) is not None:
+                    feats[idx] = fe.detect(dev, mask=img.mask)  # masks are applied on the host before the top-k: two-call path
+                else:
+                    plain.append((idx, dev))
+            for c0 in range(0, len(plain), 32):  # unmasked images: enqueued 32 at a time, no synchronisation between images
+                chunk = plain[c0:c0 + 32]
+                for (idx, _), f in zip(chunk, fe.detect_many([d for _, d in chunk])):
+                    feats[idx] = f
+            self.last_detections = len(todo)
         t_detect = time.perf_counter()
         local: Dict[Tuple[int, int], np.ndarray] = {}
         pending = []
@@ -106,7 +139,8 @@ class B200CorrespondenceGenerator(_Base):
         keypoints: List[Optional[Keypoints]] = [None] * len(images)
         for idx, f in feats.items():
             keypoints[idx] = Keypoints(f.kp.cpu().numpy(), scales=None, responses=f.score.cpu().numpy())
-        if world > 1:  # every rank returns the keypoints of all images, like the reference's gather (:83-85)
+        if world > 1 and masked:  # every rank returns the keypoints of all images, like the reference's gather (:83-85);
+            # after the feature exchange every rank already holds them all (`masked` is identical on all ranks: same image list)
             parts: List[Dict[int, Keypoints]] = [None] * world  # type: ignore[list-item]
             torch.distributed.all_gather_object(parts, {i: k for i, k in enumerate(keypoints) if k is not None})
             for part in parts:

@@ -143,13 +143,21 @@ class DeviceFrontEnd:
         between images (b2_superpoint_extract_async_dev), one at the end (b2_superpoint_finish_dev).  Images alternate between
         DETECT_LANES library contexts on as many streams, so one image's narrow kernels (80-CTA layers, the one-block top-k / scan) and
         launch gaps are filled by the other's.  Same outputs as [detect(im) for im in images]."""
+        if len(images) == 0:
+            return []
+        kp_all, score_all, desc_all, counts, shapes = self.detect_pool(images)
+        return [DeviceFeatures(kp_all[i, :n], score_all[i, :n], desc_all[i, :n], shapes[i]) for i, n in enumerate(counts)]
+
+    def detect_pool(self, images, slots: Optional[int] = None):
+        """detect_many's engine: -> (kp (slots, k, 2), score (slots, k), desc (slots, k, 256) device tensors, counts list, shapes);
+        image i fills slot i (`slots` >= len(images): padding slots for the multi-GPU feature exchange)."""
         k = self.max_keypoints
         if self._counts is None or self._counts.numel() < len(images):  # page-locked once, reused (cudaHostAlloc is slow)
             self._counts = torch.zeros(max(64, len(images)), dtype=torch.int32).pin_memory()
         counts = self._counts
         outs = []
         lanes = [(self.ctx, torch.cuda.current_stream(self.device))]
-        for j in range(1, min(DETECT_LANES, len(images))):
+        for j in range(1, min(DETECT_LANES, max(1, len(images)))):
             if len(self._lanes) < j:  # another SuperPoint instance (own work buffers) + its stream
                 ctx = _lib.Context(self.device.index or 0)
                 ctx.check(self.lib.b2_superpoint_set_weights(ctx.handle, _lib.ptr(self._sp_blob), self._sp_blob.size), "superpoint_set_weights")
@@ -158,7 +166,7 @@ class DeviceFrontEnd:
             lanes.append(self._lanes[j - 1])
         # ONE allocation per output kind for the whole list (a fresh 5 MB descriptor block per image is a cudaMalloc each when the
         # caller keeps every image's features alive: 360 of them cost 0.7 s for 120 frames), sliced per image
-        nimg = len(images)
+        nimg = max(len(images), slots or 0)
         kp_all = torch.empty((nimg, k, 2), dtype=torch.float32, device=self.device)
         score_all = torch.empty((nimg, k), dtype=torch.float32, device=self.device)
         desc_all = torch.empty((nimg, k, 256), dtype=torch.float32, device=self.device)
@@ -176,10 +184,10 @@ class DeviceFrontEnd:
                                                           NMS_RADIUS, REMOVE_BORDERS, k, _lib.ptr(kp), _lib.ptr(score), _lib.ptr(desc),
                                                           _lib.C.c_void_p(counts.data_ptr() + 4 * i), _lib.C.c_void_p(stream.cuda_stream))
             ctx.check(rc, "superpoint_extract_async_dev")
-            outs.append((kp, score, desc, (h, w)))
+            outs.append((h, w))
         for ctx, stream in lanes:
             ctx.check(self.lib.b2_superpoint_finish_dev(ctx.handle, _lib.C.c_void_p(stream.cuda_stream)), "superpoint_finish_dev")
-        return [DeviceFeatures(kp[:n], score[:n], desc[:n], hw) for (kp, score, desc, hw), n in zip(outs, counts[: len(images)].tolist())]
+        return kp_all, score_all, desc_all, counts[: len(images)].tolist(), outs
 
     def _detect_masked(self, image: torch.Tensor, h: int, w: int, ch: int, mask: np.ndarray) -> DeviceFeatures:
         cap = SuperPointEngine.capacity(h, w)

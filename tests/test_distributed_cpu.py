@@ -34,6 +34,15 @@ def _worker(rank: int, world: int, port: int, q):
         merged = D.gather_pair_results(local)
         ok_gather = sorted(merged) == pairs and all(merged[p].shape == (p[0] + 1, 2) and int(merged[p][0, 0]) == (i % world)
                                                     for i, p in enumerate(pairs))
+        # the feature exchange of the strong-scaling seam: rank r owns the images at positions r, r + world, ...
+        n, k = 3, 5
+        kp = torch.full((n, k, 2), float(rank)); sc = torch.full((n, k), 10.0 + rank); de = torch.full((n, k, 256), 20.0 + rank)
+        cnt = torch.tensor([k, rank + 1, 0], dtype=torch.int32)
+        akp, asc, ade, acnt = D.all_gather_features(kp, sc, de, cnt)
+        ok_gather = ok_gather and akp.shape == (world * n, k, 2) and acnt.tolist() == [k, 1, 0, k, 2, 0]
+        ok_gather = ok_gather and all(float(akp[r * n + j, 0, 0]) == r and float(asc[r * n + j, 0]) == 10 + r and float(ade[r * n + j, 0, 0]) == 20 + r
+                                      for r in range(world) for j in range(n))
+        ok_gather = ok_gather and [D.image_owner(i, world) for i in range(5)] == [0, 1, 0, 1, 0]
         # the bench's timing reduction: max over ranks
         t = torch.tensor([10.0 + rank], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
