@@ -2,6 +2,7 @@
 # 2-GPU evidence: gpurun --gpus 2 --timeout 1500 -- 'bash profiles/bench_r02_2gpu.sh'
 O=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+python -m pytest tests/test_multigpu_gpu.py -q 2>&1 | tail -3
 python bench.py --scaling strong --frames 120 2> $O/r02_strong_1gpu.err | grep -v "^NCCL" > $O/r02_strong_1gpu.json
 echo "strong 1 gpu: $(python -c "import json;d=json.load(open('$O/r02_strong_1gpu.json'));print(round(d['value'],1),d['strong']['phases_rank0_s'])" 2>&1 | tail -1)"
 $TR bench.py --gpus 2 --steps 3 --warmup 3 2> $O/r02_bench_2gpu.err | grep -v "^NCCL" > $O/r02_bench_vga_lightglue_2gpu.json
