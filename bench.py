@@ -68,7 +68,14 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures
 # (profiles/): per workload, or None where no capture of that workload's launch shape exists
-DOMINANT_DRAM_BYTES = {"vga_lightglue": None}
+DOMINANT_DRAM_BYTES = {
+    # profiles/r02_flash_ps.txt: the 16-problem launch (self- or cross-attention of a lock-step batch of 8 pairs at 5000 keypoints;
+    # 2 of every 3 k_flash_ps launches of this workload have that shape): 2.726 GB read + 0.086 GB written, against 0.33 GB of
+    # operands - the 64 heads of a batch do not fit L2 together, K / V tiles are re-read per 256-query block
+    "vga_lightglue": 2725897000 + 86424320,
+    # profiles/r02_conv_ps_1b.txt: conv1b, the largest of the nine k_conv_ps launch shapes (43 % of the network's FLOPs): input planes once
+    "superpoint_only": 78848256 + 5455104,
+}
 
 
 def config_of(name: str) -> dict:
@@ -574,7 +581,7 @@ def run_cuda(args):
             "data": "synthetic", "config": config_of(wname), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": w["dominant"], "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": DOMINANT_DRAM_BYTES.get(wname),
-                         "traffic_unit": "dram bytes per launch (ncu --set full capture under profiles/), null = not captured for this launch shape",
+                         "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full capture under profiles/, the launch shape named in bench.py DOMINANT_DRAM_BYTES); null = no capture of this workload's launch shape",
                          "peak_source": f"bf16_tflops_sustained ({peak_src})",
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_launches / args.steps,
                          "kernel_share_of_step": k_ms / prof_total_ms if prof_total_ms else None,
