@@ -152,8 +152,8 @@ def load_netvlad_mat(path: Union[str, Path]) -> StateDict:
     mat = scipy.io.loadmat(str(path), struct_as_record=False, squeeze_me=True)
     layers = mat["net"].layers
     sd: StateDict = {}
-    conv_layers = [l for l in layers[:30] if hasattr(l, "weights") and np.ndim(l.weights[0]) == 4][:13]
-    for idx, l in zip(NETVLAD_CONV_IDX, conv_layers):
+    for idx in NETVLAD_CONV_IDX:  # netvlad.py:116 zips backbone.children() with net.layers: same positions
+        l = layers[idx]
         sd[f"backbone.{idx}.weight"] = np.ascontiguousarray(np.transpose(np.asarray(l.weights[0], np.float32), (3, 2, 0, 1)))
         sd[f"backbone.{idx}.bias"] = np.asarray(l.weights[1], np.float32)
     sd["netvlad.score_proj.weight"] = np.ascontiguousarray(np.asarray(layers[30].weights[0], np.float32).T)[:, :, None]
