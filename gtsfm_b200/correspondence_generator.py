@@ -64,14 +64,23 @@ class B200CorrespondenceGenerator(_Base):
             return img, (img.value_array if hasattr(img, "value_array") else np.asarray(img))
 
         masked = any(getattr(im, "mask", None) is not None for im in images if not hasattr(im, "result"))
+        own = [i for i in range(len(images)) if D.image_owner(i, world) == rank]
+        own_host = []
+        if world > 1:
+            # masks take the host two-call path, and whether any image carries one must be decided by ALL ranks together (the
+            # branches below contain different collectives): each rank looks at the images it owns (Dask futures resolve here)
+            own_host = [host_image(i) for i in own]
+            flag = torch.tensor([1 if masked or any(getattr(img, "mask", None) is not None for img, _ in own_host) else 0],
+                                dtype=torch.int32, device=fe.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+            masked = bool(int(flag.item()))
         if world > 1 and not masked:
             # ONE job over several GPUs: every image is detected on exactly one rank (position mod world) and the features are
             # exchanged with one all-gather over NVLink (5 MB per image) - re-detecting on every rank whose pairs touch an image
             # made detection the part of the job that did not scale
             k = fe.max_keypoints
             n_loc = (len(images) + world - 1) // world
-            own = [i for i in range(len(images)) if D.image_owner(i, world) == rank]
-            devs = [torch.from_numpy(np.ascontiguousarray(host_image(i)[1])).to(fe.device) for i in own]
+            devs = [torch.from_numpy(np.ascontiguousarray(arr)).to(fe.device) for _, arr in own_host]
             if devs:
                 kp_l, sc_l, de_l, cnt, shapes = fe.detect_pool(devs, slots=n_loc)
             else:
